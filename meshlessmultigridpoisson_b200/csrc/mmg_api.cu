@@ -1,0 +1,816 @@
+// extern "C" layer of libmmg: argument checking, host<->device coherence at the points the
+// reference's drivers touch the data, and the V-cycle schedule (Multigrid::vCycle) as a stream of
+// kernel launches with no host synchronisation inside a cycle.
+#include <algorithm>
+#include <cstring>
+
+#include "mmg_internal.hpp"
+
+namespace mmg {
+
+static thread_local std::string g_last_error;
+
+Grid::~Grid() {
+  asm_release(*this);
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+Solver::~Solver() {
+  for (Grid* g : grids) delete g;
+  for (HybMatrix* m : restrict_) delete m;
+  for (HybMatrix* m : prolong_) delete m;
+  for (cudaEvent_t e : timers.pool) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+static void use_device(int device) { MMG_CUDA(cudaSetDevice(device)); }
+
+// device copies of the boundary lists / row flags follow the host boundaries_ and bcFlags_
+static void refresh_boundary_state(Grid& g) {
+  std::vector<int> dp, np;
+  std::vector<double> dv, nv;
+  for (const Boundary& b : g.boundaries) {
+    if (b.type == MMG_BC_DIRICHLET) { dp.insert(dp.end(), b.pts.begin(), b.pts.end()); dv.insert(dv.end(), b.vals.begin(), b.vals.end()); }
+    else if (b.type == MMG_BC_NEUMANN) { np.insert(np.end(), b.pts.begin(), b.pts.end()); nv.insert(nv.end(), b.vals.begin(), b.vals.end()); }
+  }
+  dv.resize(dp.size(), 0.0);
+  nv.resize(np.size(), 0.0);
+  g.dir_pts.upload(dp, g.stream); g.dir_vals.upload(dv, g.stream);
+  g.neu_pts.upload(np, g.stream); g.neu_vals.upload(nv, g.stream);
+  std::vector<unsigned char> rf(g.A, 0);
+  for (int i = 0; i < g.n; i++) rf[i] = (unsigned char)g.bcflags[i];
+  g.rowflag.upload(rf, g.stream);
+  g.sync();
+}
+
+static Grid* grid_create(int device, int n, const double* x, const double* y, const mmg_props* props, const double* source, int source_len,
+                         int nb, const int* b_type, const int* b_ptr, const int* b_points, const double* b_values) {
+  MMG_REQUIRE(n > 0 && x && y && props && source, MMG_ERR_ARG, "mmg_grid_create: null or empty input");
+  int ndev = 0;
+  MMG_CUDA(cudaGetDeviceCount(&ndev));
+  MMG_REQUIRE(device >= 0 && device < ndev, MMG_ERR_CUDA, "mmg_grid_create: CUDA device " + std::to_string(device) + " not available (no CPU fallback)");
+  use_device(device);
+  Grid* g = new Grid();
+  try {
+    g->device = device;
+    g->n = n;
+    g->props = *props;
+    MMG_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    g->own_stream = true;
+    g->timers = &g->own_timers;
+    g->hx.assign(x, x + n); g->hy.assign(y, y + n);
+    g->hnx.assign(n, 0.0); g->hny.assign(n, 0.0);
+    g->boundaries.resize(nb);
+    for (int i = 0; i < nb; i++) {
+      g->boundaries[i].type = b_type[i];
+      g->boundaries[i].pts.assign(b_points + b_ptr[i], b_points + b_ptr[i + 1]);
+      if (b_values) g->boundaries[i].vals.assign(b_values + b_ptr[i], b_values + b_ptr[i + 1]);
+      else g->boundaries[i].vals.assign(b_ptr[i + 1] - b_ptr[i], 0.0);
+      for (int p : g->boundaries[i].pts) MMG_REQUIRE(p >= 0 && p < n, MMG_ERR_ARG, "boundary point id out of range");
+      if (b_type[i] == MMG_BC_NEUMANN) g->neumann = true;   // setNeumannFlag(), grid.cpp:52-60
+    }
+    g->A = g->neumann ? n + 1 : n;                          // grid.cpp:17
+    MMG_REQUIRE(source_len == g->A, MMG_ERR_ARG, "source must have " + std::to_string(g->A) + " entries (n, or n+1 for a Neumann grid)");
+    g->bcflags.assign(n, 0);
+    g->diags.assign(g->A, 0.0);
+    g->x.alloc(g->A); g->x.zero(g->stream);                 // values_->setZero(), grid.cpp:22-23
+    g->x_alt.alloc(g->A); g->x_alt.zero(g->stream);
+    g->r.alloc(g->A);
+    g->b.upload(source, g->A, g->stream);
+    g->px.upload(g->hx, g->stream); g->py.upload(g->hy, g->stream);
+    g->abort_flag.alloc(1); g->abort_flag.zero(g->stream);
+    refresh_boundary_state(*g);
+  } catch (...) { delete g; throw; }
+  return g;
+}
+
+static void check_abort(Grid& g) {
+  int flag = 0;
+  g.abort_flag.download(&flag, 1, g.stream);
+  if (flag) {
+    g.abort_flag.zero(g.stream);
+    throw Error(MMG_ERR_TIMEOUT, "lexicographic sweep watchdog fired (dependency wait exceeded its limit)");
+  }
+}
+
+static void set_laplacian_csr(Grid& g, int rows, const int* ptr, const int* idx, const double* val, const double* diags, const int* nb_ptr,
+                              const int* nb_idx, const double* nb_val) {
+  MMG_REQUIRE(rows == g.A, MMG_ERR_ARG, "laplaceMat_ must have " + std::to_string(g.A) + " rows");
+  HostCsr A;
+  A.rows = rows; A.cols = rows;
+  A.ptr.assign(ptr, ptr + rows + 1);
+  A.idx.assign(idx, idx + ptr[rows]);
+  A.val.assign(val, val + ptr[rows]);
+  for (int c : A.idx) MMG_REQUIRE(c >= 0 && c < rows, MMG_ERR_ARG, "column index out of range");
+  // the parallel Neumann evaluation relies on boundary rows touching interior nodes only (grid.cpp:236,244)
+  for (int i = 0; i < g.n; i++)
+    if (g.bcflags[i] == MMG_BC_NEUMANN)
+      for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+        MMG_REQUIRE(A.idx[k] == i || (A.idx[k] < g.n && g.bcflags[A.idx[k]] == 0), MMG_ERR_ARG,
+                    "a Neumann row couples to another boundary node; bound_eval_neumann would be order dependent");
+  hyb_from_csr(g.Lap, A, /*diag_first=*/true, /*has_reg=*/g.neumann, g.stream);
+  if (diags) g.diags.assign(diags, diags + g.A);
+  g.nbc = HostCsr();
+  if (nb_ptr) {
+    g.nbc.rows = g.nbc.cols = rows;
+    g.nbc.ptr.assign(nb_ptr, nb_ptr + rows + 1);
+    g.nbc.idx.assign(nb_idx, nb_idx + nb_ptr[rows]);
+    g.nbc.val.assign(nb_val, nb_val + nb_ptr[rows]);
+  }
+  g.have_laplacian = true;
+  g.have_colours = false;
+}
+
+// Grid::push_inhomog_to_rhs grid.cpp:664-685 — O(|boundary| * stencil) entries; done through a host round trip of
+// the touched source entries only when the Laplacian came from the upload path (device path: assembly.cu).
+static void push_inhomog_to_rhs(Grid& g) {
+  if (!g.implicit) return;
+  if (g.nbc.rows == 0 || g.nbc.idx.empty()) return;
+  std::vector<double> src(g.A);
+  g.b.download(src.data(), g.A, g.stream);
+  const std::vector<double> copy = src;
+  for (int i = 0; i < g.n; i++) {
+    if (g.bcflags[i] != 0) continue;
+    for (int j = g.nbc.ptr[i]; j < g.nbc.ptr[i + 1]; j++) {
+      const double diag = g.diags[g.nbc.idx[j]];
+      const double A_ij = g.nbc.val[j];
+      src[i] -= A_ij * copy[g.nbc.idx[j]] / diag;
+    }
+  }
+  g.b.upload(src.data(), g.A, g.stream);
+  g.sync();
+}
+
+// ---- Multigrid::vCycle multigrid.cpp:62-110 / FracStepMultigrid.cpp:60-112 ---------------------------
+static void vcycle(Solver& s) {
+  const size_t L = s.grids.size();
+  MMG_REQUIRE(L >= 1, MMG_ERR_STATE, "vCycle: no grids");
+  Grid* cur = s.grids[L - 1];
+  if (s.flavour == MMG_FLAVOUR_FRACSTEP && L == 1) { op_sor(*cur, s.smoother); return; }  // FracStepMultigrid.cpp:64-67
+  for (size_t i = 1; i < L; i++) MMG_REQUIRE(s.restrict_[i] && s.prolong_[i - 1], MMG_ERR_STATE, "vCycle: buildMatrices() has not run");
+  if ((size_t)s.hist_len >= s.hist.n) {
+    DevBuf<double> bigger;
+    bigger.alloc(std::max<size_t>(1024, s.hist.n * 2));
+    if (s.hist_len) MMG_CUDA(cudaMemcpyAsync(bigger.p, s.hist.p, sizeof(double) * s.hist_len, cudaMemcpyDeviceToDevice, s.stream));
+    MMG_CUDA(cudaStreamSynchronize(s.stream));
+    s.hist = std::move(bigger);
+  }
+  op_residual_norm(*cur, s.hist.p + s.hist_len);   // residuals_.push_back(residual()), :66-67
+  s.hist_len++;
+  op_bound_eval_neumann(*cur);                      // :68
+  for (size_t i = L - 1; i > 0; i--) {              // :71-88
+    cur = s.grids[i];
+    Grid* coarse = s.grids[i - 1];
+    if (i != L - 1) op_zero_values(*cur);
+    op_boundary_op(*cur, i == L - 1 ? MMG_FINE : MMG_COARSE);
+    op_sor(*cur, s.smoother);
+    op_residual(*cur, cur->r.p);
+    op_restrict(*cur, *coarse, *s.restrict_[i], cur->r.p);
+  }
+  op_boundary_op(*cur, MMG_COARSE);                 // quirk kept: still grid 1 (or the only grid), :91
+  cur = s.grids[0];
+  op_zero_values(*cur);
+  op_sor(*cur, s.smoother);
+  op_sor(*cur, s.smoother);
+  for (size_t i = 1; i < L; i++) {                  // :99-109
+    cur = s.grids[i];
+    op_prolong_correct(*cur, *s.grids[i - 1], *s.prolong_[i - 1]);
+    op_sor(*cur, s.smoother);
+  }
+}
+
+static void solver_check_abort(Solver& s) {
+  for (Grid* g : s.grids) check_abort(*g);
+}
+
+static void fetch_history(Solver& s) {
+  s.hist_host.resize(s.hist_len);
+  if (s.hist_len) s.hist.download(s.hist_host.data(), s.hist_len, s.stream);
+}
+
+}  // namespace mmg
+
+using namespace mmg;
+
+#define API_BEGIN try {
+#define API_END                                    \
+    return MMG_OK;                                 \
+  } catch (const mmg::Error& e) {                  \
+    mmg::g_last_error = e.what();                  \
+    return e.code;                                 \
+  } catch (const std::exception& e) {              \
+    mmg::g_last_error = e.what();                  \
+    return MMG_ERR_STATE;                          \
+  }
+#define G(ptr) (*reinterpret_cast<mmg::Grid*>(ptr))
+#define S(ptr) (*reinterpret_cast<mmg::Solver*>(ptr))
+#define NEED(p) MMG_REQUIRE((p) != nullptr, MMG_ERR_ARG, std::string(__func__) + ": null argument " #p)
+
+extern "C" {
+
+const char* mmg_last_error(void) { return mmg::g_last_error.c_str(); }
+const char* mmg_build_info(void) { return "libmmg sm_100a (compute_100a) CUDA " MMG_STR(__CUDACC_VER_MAJOR__) "." MMG_STR(__CUDACC_VER_MINOR__) " — no CPU fallback"; }
+
+int mmg_device_count(int* count) {
+  API_BEGIN
+  NEED(count);
+  *count = 0;
+  MMG_CUDA(cudaGetDeviceCount(count));
+  API_END
+}
+
+int mmg_grid_create(mmg_grid** out, int device, int n, const double* x, const double* y, const mmg_props* props, const double* source,
+                    int source_len, int n_boundaries, const int* b_type, const int* b_ptr, const int* b_points, const double* b_values) {
+  API_BEGIN
+  NEED(out);
+  MMG_REQUIRE(n_boundaries == 0 || (b_type && b_ptr && b_points), MMG_ERR_ARG, "mmg_grid_create: boundary arrays missing");
+  *out = reinterpret_cast<mmg_grid*>(grid_create(device, n, x, y, props, source, source_len, n_boundaries, b_type, b_ptr, b_points, b_values));
+  API_END
+}
+int mmg_grid_destroy(mmg_grid* g) {
+  API_BEGIN
+  if (g) { use_device(G(g).device); delete &G(g); }
+  API_END
+}
+int mmg_grid_set_implicit(mmg_grid* g, int flag) {
+  API_BEGIN
+  NEED(g);
+  G(g).implicit = flag != 0;
+  API_END
+}
+int mmg_grid_set_bc_flag(mmg_grid* g, int boundary, int type, const double* values, int n_values) {
+  API_BEGIN
+  NEED(g);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  MMG_REQUIRE(boundary >= 0 && boundary < (int)gr.boundaries.size(), MMG_ERR_ARG, "setBCFlag: no such boundary");
+  MMG_REQUIRE(type == MMG_BC_DIRICHLET || type == MMG_BC_NEUMANN, MMG_ERR_ARG, "setBCFlag: type must be dirichlet(1) or neumann(2)");
+  Boundary& b = gr.boundaries[boundary];
+  MMG_REQUIRE((type == MMG_BC_NEUMANN) == gr.neumann || !gr.neumann || type == MMG_BC_DIRICHLET, MMG_ERR_ARG,
+              "setBCFlag: a Neumann type must already be present at construction (Grid ctor sizes the system from it)");
+  MMG_REQUIRE(type != MMG_BC_NEUMANN || gr.neumann, MMG_ERR_ARG, "setBCFlag: grid was constructed without a Neumann boundary");
+  b.type = type;
+  for (int p : b.pts) gr.bcflags[p] = type;
+  if (values) { MMG_REQUIRE(n_values == (int)b.pts.size(), MMG_ERR_ARG, "setBCFlag: value count differs from the boundary's point count"); b.vals.assign(values, values + n_values); }
+  refresh_boundary_state(gr);
+  API_END
+}
+int mmg_grid_build_normal_vecs_square(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  Grid& gr = G(g);
+  MMG_REQUIRE(!gr.boundaries.empty(), MMG_ERR_STATE, "build_normal_vecs: no boundary");
+  for (int p : gr.boundaries[0].pts) {  // grid.cpp:445-461: boundaries_[0] only, y tested first, inward normals
+    const double x = gr.hx[p], y = gr.hy[p];
+    if (y == 0) { gr.hnx[p] = 0; gr.hny[p] = 1; }
+    else if (y == 1) { gr.hnx[p] = 0; gr.hny[p] = -1; }
+    else if (x == 0) { gr.hnx[p] = 1; gr.hny[p] = 0; }
+    else if (x == 1) { gr.hnx[p] = -1; gr.hny[p] = 0; }
+  }
+  API_END
+}
+int mmg_grid_set_normal_vecs(mmg_grid* g, const double* nx, const double* ny) {
+  API_BEGIN
+  NEED(g); NEED(nx); NEED(ny);
+  G(g).hnx.assign(nx, nx + G(g).n); G(g).hny.assign(ny, ny + G(g).n);
+  API_END
+}
+int mmg_grid_rcm_order_points(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  asm_rcm_order_points(G(g));
+  refresh_boundary_state(G(g));
+  API_END
+}
+int mmg_grid_build_deriv_normal_bound(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  asm_build_deriv_normal_bound(G(g));
+  API_END
+}
+int mmg_grid_build_laplacian(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  asm_build_laplacian(G(g));
+  API_END
+}
+int mmg_grid_modify_coeff_neumann(mmg_grid* g, int coarse) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  op_modify_coeff_neumann(G(g), coarse);
+  API_END
+}
+int mmg_grid_push_inhomog_to_rhs(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  push_inhomog_to_rhs(G(g));
+  API_END
+}
+int mmg_grid_boundary_op(mmg_grid* g, int coarse) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  op_boundary_op(G(g), coarse);
+  API_END
+}
+int mmg_grid_bound_eval_neumann(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  op_bound_eval_neumann(G(g));
+  API_END
+}
+int mmg_grid_sor(mmg_grid* g, int smoother) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  op_sor(G(g), smoother);
+  G(g).sync();
+  check_abort(G(g));
+  API_END
+}
+int mmg_grid_residual(mmg_grid* g, double* out) {
+  API_BEGIN
+  NEED(g); NEED(out);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  op_residual(gr, gr.r.p);
+  gr.r.download(out, gr.A, gr.stream);
+  API_END
+}
+int mmg_grid_fix_vector_bound_coarse(mmg_grid* g, double* vec) {
+  API_BEGIN
+  NEED(g); NEED(vec);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  DevBuf<double> t;
+  t.upload(vec, gr.A, gr.stream);
+  op_fix_vector_bound_coarse(gr, t.p);
+  t.download(vec, gr.A, gr.stream);
+  API_END
+}
+int mmg_grid_knn(mmg_grid* g, int m, const double* qx, const double* qy, const int* q_bcflag, int neumann, int k, int* out) {
+  API_BEGIN
+  NEED(g); NEED(qx); NEED(qy); NEED(out);
+  use_device(G(g).device);
+  asm_knn_points(G(g), m, qx, qy, q_bcflag, neumann, k, out);
+  API_END
+}
+int mmg_grid_weights(mmg_grid* g, int which, int m, const int* ids, double* w, int* nb) {
+  API_BEGIN
+  NEED(g); NEED(ids); NEED(w); NEED(nb);
+  use_device(G(g).device);
+  asm_weights(G(g), which, m, ids, w, nb);
+  API_END
+}
+int mmg_grid_point_interp_weights(mmg_grid* g, int m, const double* px, const double* py, int polyDeg, double* w, int* nb) {
+  API_BEGIN
+  NEED(g); NEED(px); NEED(py); NEED(w); NEED(nb);
+  use_device(G(g).device);
+  asm_point_interp_weights(G(g), m, px, py, polyDeg, w, nb);
+  API_END
+}
+int mmg_grid_sizes(mmg_grid* g, int* n, int* a_size, int* neumann_flag) {
+  API_BEGIN
+  NEED(g);
+  if (n) *n = G(g).n;
+  if (a_size) *a_size = G(g).A;
+  if (neumann_flag) *neumann_flag = G(g).neumann;
+  API_END
+}
+int mmg_grid_get_values(mmg_grid* g, double* out) {
+  API_BEGIN
+  NEED(g); NEED(out);
+  use_device(G(g).device);
+  G(g).x.download(out, G(g).A, G(g).stream);
+  API_END
+}
+int mmg_grid_set_values(mmg_grid* g, const double* in) {
+  API_BEGIN
+  NEED(g); NEED(in);
+  use_device(G(g).device);
+  MMG_CUDA(cudaMemcpyAsync(G(g).x.p, in, sizeof(double) * G(g).A, cudaMemcpyHostToDevice, G(g).stream));
+  G(g).sync();
+  API_END
+}
+int mmg_grid_get_source(mmg_grid* g, double* out) {
+  API_BEGIN
+  NEED(g); NEED(out);
+  use_device(G(g).device);
+  G(g).b.download(out, G(g).A, G(g).stream);
+  API_END
+}
+int mmg_grid_set_source(mmg_grid* g, const double* in) {
+  API_BEGIN
+  NEED(g); NEED(in);
+  use_device(G(g).device);
+  MMG_CUDA(cudaMemcpyAsync(G(g).b.p, in, sizeof(double) * G(g).A, cudaMemcpyHostToDevice, G(g).stream));
+  G(g).sync();
+  API_END
+}
+int mmg_grid_get_points(mmg_grid* g, double* x, double* y) {
+  API_BEGIN
+  NEED(g); NEED(x); NEED(y);
+  std::memcpy(x, G(g).hx.data(), sizeof(double) * G(g).n);
+  std::memcpy(y, G(g).hy.data(), sizeof(double) * G(g).n);
+  API_END
+}
+int mmg_grid_get_bcflags(mmg_grid* g, int* flags) {
+  API_BEGIN
+  NEED(g); NEED(flags);
+  std::memcpy(flags, G(g).bcflags.data(), sizeof(int) * G(g).n);
+  API_END
+}
+int mmg_grid_get_normals(mmg_grid* g, double* nx, double* ny) {
+  API_BEGIN
+  NEED(g); NEED(nx); NEED(ny);
+  std::memcpy(nx, G(g).hnx.data(), sizeof(double) * G(g).n);
+  std::memcpy(ny, G(g).hny.data(), sizeof(double) * G(g).n);
+  API_END
+}
+int mmg_grid_get_diags(mmg_grid* g, double* out) {
+  API_BEGIN
+  NEED(g); NEED(out);
+  std::memcpy(out, G(g).diags.data(), sizeof(double) * G(g).A);
+  API_END
+}
+int mmg_grid_get_perm(mmg_grid* g, int* order) {
+  API_BEGIN
+  NEED(g); NEED(order);
+  MMG_REQUIRE((int)G(g).order.size() == G(g).n, MMG_ERR_STATE, "rcm_order_points has not run on this grid");
+  std::memcpy(order, G(g).order.data(), sizeof(int) * G(g).n);
+  API_END
+}
+int mmg_grid_get_boundary(mmg_grid* g, int boundary, int* type, int* count, int* points, double* values) {
+  API_BEGIN
+  NEED(g);
+  MMG_REQUIRE(boundary >= 0 && boundary < (int)G(g).boundaries.size(), MMG_ERR_ARG, "no such boundary");
+  const Boundary& b = G(g).boundaries[boundary];
+  if (type) *type = b.type;
+  if (count) *count = (int)b.pts.size();
+  if (points) std::memcpy(points, b.pts.data(), sizeof(int) * b.pts.size());
+  if (values) std::memcpy(values, b.vals.data(), sizeof(double) * b.vals.size());
+  API_END
+}
+static void grid_csr(Grid& gr, int which, HostCsr& A) {
+  if (which == MMG_MAT_LAPLACE) {
+    MMG_REQUIRE(gr.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+    hyb_to_csr(gr.Lap, A, gr.stream);
+  } else if (which == MMG_MAT_NEUMANN_COEFFS) {
+    A = gr.nbc;
+    if (A.rows == 0) { A.rows = A.cols = gr.A; A.ptr.assign(gr.A + 1, 0); }
+  } else {
+    throw Error(MMG_ERR_ARG, "matrix selector not available on a grid");
+  }
+}
+int mmg_grid_csr_nnz(mmg_grid* g, int which, int64_t* nnz) {
+  API_BEGIN
+  NEED(g); NEED(nnz);
+  use_device(G(g).device);
+  if (which == MMG_MAT_LAPLACE) { MMG_REQUIRE(G(g).have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded"); *nnz = G(g).Lap.nnz; }
+  else { HostCsr A; grid_csr(G(g), which, A); *nnz = A.nnz(); }
+  API_END
+}
+int mmg_grid_get_csr(mmg_grid* g, int which, int* ptr, int* idx, double* val) {
+  API_BEGIN
+  NEED(g); NEED(ptr); NEED(idx); NEED(val);
+  use_device(G(g).device);
+  HostCsr A;
+  grid_csr(G(g), which, A);
+  std::memcpy(ptr, A.ptr.data(), sizeof(int) * A.ptr.size());
+  std::memcpy(idx, A.idx.data(), sizeof(int) * A.idx.size());
+  std::memcpy(val, A.val.data(), sizeof(double) * A.val.size());
+  API_END
+}
+int mmg_grid_set_laplacian_csr(mmg_grid* g, int rows, const int* ptr, const int* idx, const double* val, const double* diags, const int* nb_ptr,
+                               const int* nb_idx, const double* nb_val) {
+  API_BEGIN
+  NEED(g); NEED(ptr); NEED(idx); NEED(val);
+  use_device(G(g).device);
+  set_laplacian_csr(G(g), rows, ptr, idx, val, diags, nb_ptr, nb_idx, nb_val);
+  API_END
+}
+int mmg_grid_get_colouring(mmg_grid* g, int* n_colours, int* colour) {
+  API_BEGIN
+  NEED(g); NEED(n_colours); NEED(colour);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  MMG_REQUIRE(gr.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+  if (!gr.have_colours) build_colouring(gr);
+  *n_colours = gr.n_colours;
+  std::memcpy(colour, gr.colour_host.data(), sizeof(int) * gr.A);
+  API_END
+}
+int mmg_grid_get_lex_levels(mmg_grid* g, int* n_levels, int* level) {
+  API_BEGIN
+  NEED(g); NEED(n_levels); NEED(level);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  MMG_REQUIRE(gr.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+  std::vector<int> lv;
+  compute_lex_levels(gr, lv, *n_levels);
+  std::memcpy(level, lv.data(), sizeof(int) * gr.A);
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------ solver
+int mmg_solver_create(mmg_solver** out, int flavour) {
+  API_BEGIN
+  NEED(out);
+  MMG_REQUIRE(flavour == MMG_FLAVOUR_MULTIGRID || flavour == MMG_FLAVOUR_FRACSTEP, MMG_ERR_ARG, "unknown solver flavour");
+  Solver* s = new Solver();
+  s->flavour = flavour;
+  *out = reinterpret_cast<mmg_solver*>(s);
+  API_END
+}
+int mmg_solver_destroy(mmg_solver* s) {
+  API_BEGIN
+  if (s) {
+    if (!S(s).grids.empty()) use_device(S(s).grids[0]->device);
+    delete &S(s);
+  }
+  API_END
+}
+int mmg_solver_add_grid(mmg_solver* s, mmg_grid* g) {
+  API_BEGIN
+  NEED(s); NEED(g);
+  Solver& so = S(s);
+  Grid* gr = &G(g);
+  use_device(gr->device);
+  if (!so.stream) MMG_CUDA(cudaStreamCreateWithFlags(&so.stream, cudaStreamNonBlocking));
+  gr->sync();
+  if (gr->own_stream) { cudaStreamDestroy(gr->stream); gr->own_stream = false; }
+  gr->stream = so.stream;               // one stream for the whole cycle
+  gr->timers = &so.timers;
+  so.grids.push_back(gr);
+  std::sort(so.grids.begin(), so.grids.end(), [](Grid* a, Grid* b) { return a->n != b->n ? a->n < b->n : a < b; });  // multigrid.cpp:116-122
+  for (HybMatrix* m : so.restrict_) delete m;
+  for (HybMatrix* m : so.prolong_) delete m;
+  so.restrict_.assign(so.grids.size(), nullptr);
+  so.prolong_.assign(so.grids.size(), nullptr);
+  API_END
+}
+int mmg_solver_num_grids(mmg_solver* s, int* n) {
+  API_BEGIN
+  NEED(s); NEED(n);
+  *n = (int)S(s).grids.size();
+  API_END
+}
+int mmg_solver_grid(mmg_solver* s, int level, mmg_grid** g) {
+  API_BEGIN
+  NEED(s); NEED(g);
+  MMG_REQUIRE(level >= 0 && level < (int)S(s).grids.size(), MMG_ERR_ARG, "no such level");
+  *g = reinterpret_cast<mmg_grid*>(S(s).grids[level]);
+  API_END
+}
+int mmg_solver_finish_build(mmg_solver* s) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  for (size_t i = 0; i + 1 < so.grids.size(); i++) { use_device(so.grids[i]->device); op_modify_coeff_neumann(*so.grids[i], MMG_COARSE); }  // multigrid.cpp:54-59
+  API_END
+}
+int mmg_solver_build_matrices(mmg_solver* s) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  const size_t L = so.grids.size();
+  MMG_REQUIRE(L >= 1, MMG_ERR_STATE, "buildMatrices: no grids");
+  use_device(so.grids[0]->device);
+  const int finepoly = so.grids[L - 1]->props.polyDeg;
+  for (size_t i = 0; i + 1 < L; i++) {   // buildProlongMatrices multigrid.cpp:34-40: base = level i, target = level i+1
+    delete so.prolong_[i];
+    so.prolong_[i] = new HybMatrix();
+    const int poly = so.flavour == MMG_FLAVOUR_FRACSTEP ? so.grids[i]->props.polyDeg : finepoly;  // FracStepMultigrid.cpp:23 vs multigrid.cpp:22,25
+    asm_build_interp(*so.grids[i], *so.grids[i + 1], poly, *so.prolong_[i]);
+  }
+  for (size_t i = 1; i < L; i++) {       // buildRestrictionMatrices multigrid.cpp:41-47: base = level i, target = level i-1
+    delete so.restrict_[i];
+    so.restrict_[i] = new HybMatrix();
+    const int poly = so.flavour == MMG_FLAVOUR_FRACSTEP ? so.grids[i]->props.polyDeg : finepoly;
+    asm_build_interp(*so.grids[i], *so.grids[i - 1], poly, *so.restrict_[i]);
+  }
+  for (size_t i = 0; i + 1 < L; i++) op_modify_coeff_neumann(*so.grids[i], MMG_COARSE);
+  API_END
+}
+int mmg_solver_set_interp_csr(mmg_solver* s, int which, int level, int rows, int cols, const int* ptr, const int* idx, const double* val) {
+  API_BEGIN
+  NEED(s); NEED(ptr); NEED(idx); NEED(val);
+  Solver& so = S(s);
+  MMG_REQUIRE(level >= 0 && level < (int)so.grids.size(), MMG_ERR_ARG, "no such level");
+  MMG_REQUIRE(which == MMG_MAT_RESTRICT || which == MMG_MAT_PROLONG, MMG_ERR_ARG, "which must be MMG_MAT_RESTRICT or MMG_MAT_PROLONG");
+  use_device(so.grids[level]->device);
+  HostCsr A;
+  A.rows = rows; A.cols = cols;
+  A.ptr.assign(ptr, ptr + rows + 1);
+  A.idx.assign(idx, idx + ptr[rows]);
+  A.val.assign(val, val + ptr[rows]);
+  for (int c : A.idx) MMG_REQUIRE(c >= 0 && c < cols, MMG_ERR_ARG, "column index out of range");
+  std::vector<HybMatrix*>& dst = which == MMG_MAT_RESTRICT ? so.restrict_ : so.prolong_;
+  delete dst[level];
+  dst[level] = new HybMatrix();
+  hyb_from_csr(*dst[level], A, false, false, so.stream);
+  API_END
+}
+static HybMatrix* interp_of(Solver& so, int which, int level) {
+  MMG_REQUIRE(level >= 0 && level < (int)so.grids.size(), MMG_ERR_ARG, "no such level");
+  MMG_REQUIRE(which == MMG_MAT_RESTRICT || which == MMG_MAT_PROLONG, MMG_ERR_ARG, "which must be MMG_MAT_RESTRICT or MMG_MAT_PROLONG");
+  HybMatrix* m = which == MMG_MAT_RESTRICT ? so.restrict_[level] : so.prolong_[level];
+  MMG_REQUIRE(m != nullptr, MMG_ERR_STATE, "that interpolation matrix does not exist (NULL in the reference too) or is not built");
+  return m;
+}
+int mmg_solver_interp_nnz(mmg_solver* s, int which, int level, int* rows, int* cols, int64_t* nnz) {
+  API_BEGIN
+  NEED(s);
+  HybMatrix* m = interp_of(S(s), which, level);
+  if (rows) *rows = m->rows;
+  if (cols) *cols = m->cols;
+  if (nnz) *nnz = m->nnz;
+  API_END
+}
+int mmg_solver_get_interp_csr(mmg_solver* s, int which, int level, int* ptr, int* idx, double* val) {
+  API_BEGIN
+  NEED(s); NEED(ptr); NEED(idx); NEED(val);
+  Solver& so = S(s);
+  HybMatrix* m = interp_of(so, which, level);
+  use_device(so.grids[level]->device);
+  HostCsr A;
+  hyb_to_csr(*m, A, so.stream);
+  std::memcpy(ptr, A.ptr.data(), sizeof(int) * A.ptr.size());
+  std::memcpy(idx, A.idx.data(), sizeof(int) * A.idx.size());
+  std::memcpy(val, A.val.data(), sizeof(double) * A.val.size());
+  API_END
+}
+int mmg_solver_set_smoother(mmg_solver* s, int smoother) {
+  API_BEGIN
+  NEED(s);
+  MMG_REQUIRE(smoother == MMG_SMOOTHER_LEXICOGRAPHIC || smoother == MMG_SMOOTHER_MULTICOLOUR, MMG_ERR_ARG, "unknown smoother");
+  S(s).smoother = smoother;
+  API_END
+}
+int mmg_solver_restrict(mmg_solver* s, int level) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  MMG_REQUIRE(level >= 1 && level < (int)so.grids.size() && so.restrict_[level], MMG_ERR_ARG, "restrict: level must be >= 1 with a built restriction matrix");
+  Grid& fine = *so.grids[level];
+  use_device(fine.device);
+  op_residual(fine, fine.r.p);
+  op_restrict(fine, *so.grids[level - 1], *so.restrict_[level], fine.r.p);
+  MMG_CUDA(cudaStreamSynchronize(so.stream));
+  API_END
+}
+int mmg_solver_prolong_correct(mmg_solver* s, int level) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  MMG_REQUIRE(level >= 1 && level < (int)so.grids.size() && so.prolong_[level - 1], MMG_ERR_ARG, "prolong: level must be >= 1 with a built prolongation matrix");
+  use_device(so.grids[level]->device);
+  op_prolong_correct(*so.grids[level], *so.grids[level - 1], *so.prolong_[level - 1]);
+  MMG_CUDA(cudaStreamSynchronize(so.stream));
+  API_END
+}
+int mmg_solver_coarse_solve(mmg_solver* s) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  MMG_REQUIRE(!so.grids.empty(), MMG_ERR_STATE, "coarse_solve: no grids");
+  Grid& c = *so.grids[0];
+  use_device(c.device);
+  op_zero_values(c);
+  op_sor(c, so.smoother);
+  op_sor(c, so.smoother);
+  MMG_CUDA(cudaStreamSynchronize(so.stream));
+  solver_check_abort(so);
+  API_END
+}
+int mmg_solver_vcycle(mmg_solver* s, int n_cycles) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  MMG_REQUIRE(!so.grids.empty(), MMG_ERR_STATE, "vCycle: no grids");
+  use_device(so.grids[0]->device);
+  for (int i = 0; i < n_cycles; i++) vcycle(so);
+  MMG_CUDA(cudaStreamSynchronize(so.stream));
+  solver_check_abort(so);
+  API_END
+}
+int mmg_solver_time_vcycles(mmg_solver* s, int n_cycles, double* ms) {
+  API_BEGIN
+  NEED(s); NEED(ms);
+  Solver& so = S(s);
+  MMG_REQUIRE(!so.grids.empty(), MMG_ERR_STATE, "vCycle: no grids");
+  use_device(so.grids[0]->device);
+  cudaEvent_t e0, e1;
+  MMG_CUDA(cudaEventCreate(&e0)); MMG_CUDA(cudaEventCreate(&e1));
+  MMG_CUDA(cudaStreamSynchronize(so.stream));
+  MMG_CUDA(cudaEventRecord(e0, so.stream));
+  for (int i = 0; i < n_cycles; i++) vcycle(so);
+  MMG_CUDA(cudaEventRecord(e1, so.stream));
+  MMG_CUDA(cudaEventSynchronize(e1));
+  float t = 0;
+  MMG_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  *ms = t;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  solver_check_abort(so);
+  API_END
+}
+int mmg_solver_residual(mmg_solver* s, double* out) {
+  API_BEGIN
+  NEED(s); NEED(out);
+  Solver& so = S(s);
+  MMG_REQUIRE(!so.grids.empty(), MMG_ERR_STATE, "residual: no grids");
+  Grid& fine = *so.grids.back();
+  use_device(fine.device);
+  DevBuf<double> ratio;
+  ratio.alloc(1);
+  op_residual_norm(fine, ratio.p);
+  ratio.download(out, 1, so.stream);
+  API_END
+}
+int mmg_solver_history_len(mmg_solver* s, int* n) {
+  API_BEGIN
+  NEED(s); NEED(n);
+  *n = S(s).hist_len;
+  API_END
+}
+int mmg_solver_get_history(mmg_solver* s, double* out, int cap) {
+  API_BEGIN
+  NEED(s); NEED(out);
+  Solver& so = S(s);
+  if (!so.grids.empty()) use_device(so.grids[0]->device);
+  fetch_history(so);
+  for (int i = 0; i < so.hist_len && i < cap; i++) out[i] = so.hist_host[i];
+  API_END
+}
+int mmg_solver_solve(mmg_solver* s, double tol, int max_cycles, int extra_bound_eval, int* cycles_done, double* final_residual) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  MMG_REQUIRE(!so.grids.empty(), MMG_ERR_STATE, "solve: no grids");
+  Grid& fine = *so.grids.back();
+  use_device(fine.device);
+  DevBuf<double> ratio;
+  ratio.alloc(1);
+  int n = 0;
+  double r = 0;
+  while (true) {                       // while (mg.residual() >= tol) { mg.vCycle(); [bound_eval_neumann();] }
+    op_residual_norm(fine, ratio.p);
+    ratio.download(&r, 1, so.stream);
+    if (!(r >= tol) || n >= max_cycles) break;
+    vcycle(so);
+    if (extra_bound_eval) op_bound_eval_neumann(fine);
+    n++;
+  }
+  MMG_CUDA(cudaStreamSynchronize(so.stream));
+  solver_check_abort(so);
+  if (cycles_done) *cycles_done = n;
+  if (final_residual) *final_residual = r;
+  API_END
+}
+int mmg_solver_sync(mmg_solver* s) {
+  API_BEGIN
+  NEED(s);
+  if (S(s).stream) MMG_CUDA(cudaStreamSynchronize(S(s).stream));
+  API_END
+}
+int mmg_solver_enable_timers(mmg_solver* s, int on) {
+  API_BEGIN
+  NEED(s);
+  S(s).timers.on = on != 0;
+  API_END
+}
+int mmg_solver_get_timers(mmg_solver* s, double* ms, int64_t* launches, int64_t* bytes) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  if (so.stream) MMG_CUDA(cudaStreamSynchronize(so.stream));
+  timers_collect(so.timers);
+  for (int i = 0; i < MMG_T_COUNT; i++) {
+    if (ms) ms[i] = so.timers.ms[i];
+    if (launches) launches[i] = so.timers.launches[i];
+    if (bytes) bytes[i] = so.timers.bytes[i];
+  }
+  API_END
+}
+int mmg_solver_reset_timers(mmg_solver* s) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  if (so.stream) MMG_CUDA(cudaStreamSynchronize(so.stream));
+  timers_collect(so.timers);
+  for (int i = 0; i < MMG_T_COUNT; i++) { so.timers.ms[i] = 0; so.timers.launches[i] = 0; so.timers.bytes[i] = 0; }
+  API_END
+}
+int mmg_solver_launch_count(mmg_solver* s, int64_t* launches) {
+  API_BEGIN
+  NEED(s); NEED(launches);
+  *launches = S(s).timers.total_launches;
+  API_END
+}
+
+}  // extern "C"

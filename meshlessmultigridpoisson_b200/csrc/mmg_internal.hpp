@@ -1,0 +1,229 @@
+// Internal structures of libmmg (sm_100a).  Host-side C++ only; kernels live in the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/mmg.h"
+
+#define MMG_STR2(x) #x
+#define MMG_STR(x) MMG_STR2(x)
+
+namespace mmg {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define MMG_CUDA(call)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t e__ = (call);                                                                                  \
+    if (e__ != cudaSuccess)                                                                                    \
+      throw ::mmg::Error(MMG_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e__) + " at " + \
+                                           __FILE__ + ":" + std::to_string(__LINE__));                          \
+  } while (0)
+#define MMG_REQUIRE(cond, code, msg) \
+  do {                               \
+    if (!(cond)) throw ::mmg::Error(code, msg); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) MMG_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+  }
+  void zero(cudaStream_t s) { if (n) MMG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    if (count != n) alloc(count);
+    if (count) MMG_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void download(T* h, size_t count, cudaStream_t s) const {
+    if (count) MMG_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    MMG_CUDA(cudaStreamSynchronize(s));
+  }
+  std::vector<T> to_host(cudaStream_t s) const { std::vector<T> h(n); download(h.data(), n, s); return h; }
+};
+
+// Host CSR as Eigen leaves it: compressed rows, columns ascending, explicit zeros kept.
+struct HostCsr {
+  int rows = 0, cols = 0;
+  std::vector<int> ptr, idx;
+  std::vector<double> val;
+  int64_t nnz() const { return (int64_t)idx.size(); }
+};
+
+// Device view of a "row-chunk HYB" matrix:
+//   row r owns one 32-byte-aligned chunk [ W x fp64 values | W x int32 columns | pad ], its first
+//   min(len,W) entries; when diag_first the diagonal sits in slot 0 and the rest stay in ascending
+//   column order.  Rows longer than W spill the tail into a small CSR (ovf_*), found by binary search
+//   over ovf_rows.  The dense regularisation row of a Neumann grid (grid.cpp:570-576) is kept apart
+//   (reg_*), because it is a global reduction rather than a stencil row.
+struct HybView {
+  const unsigned char* chunks;
+  size_t chunk_bytes;
+  int W;
+  int rows;        // rows stored as chunks (excludes the regularisation row)
+  const int* len;  // stored entries per row (may exceed W)
+  int n_ovf;
+  const int* ovf_rows;
+  const int* ovf_ptr;
+  const int* ovf_col;
+  const double* ovf_val;
+};
+
+struct HybMatrix {
+  int rows = 0, cols = 0, W = 0;
+  size_t chunk_bytes = 0;
+  bool diag_first = false;
+  int64_t nnz = 0;  // stored entries incl. the regularisation row
+  DevBuf<unsigned char> chunks;
+  DevBuf<int> len;
+  int n_ovf = 0;
+  DevBuf<int> ovf_rows, ovf_ptr, ovf_col;
+  DevBuf<double> ovf_val;
+  // regularisation row (index reg_row == rows when present, -1 otherwise); diagonal excluded from reg_col/val
+  int reg_row = -1;
+  int reg_len = 0;
+  double reg_diag = 0;
+  DevBuf<int> reg_col;
+  DevBuf<double> reg_val;
+  HybView view() const {
+    return HybView{chunks.p, chunk_bytes, W, rows, len.p, n_ovf, ovf_rows.p, ovf_ptr.p, ovf_col.p, ovf_val.p};
+  }
+  // algorithmic bytes of one pass over the matrix: 12 B per stored entry
+  int64_t matrix_bytes() const { return nnz * 12; }
+};
+
+// Build the device HYB from a host CSR.  has_reg: the last row is the dense regularisation row.
+void hyb_from_csr(HybMatrix& M, const HostCsr& A, bool diag_first, bool has_reg, cudaStream_t s);
+// Rebuild the host CSR (Eigen order) from the device HYB.
+void hyb_to_csr(const HybMatrix& M, HostCsr& A, cudaStream_t s);
+
+struct Boundary {
+  int type = 0;
+  std::vector<int> pts;
+  std::vector<double> vals;
+};
+
+struct Timers {
+  bool on = false;
+  double ms[MMG_T_COUNT] = {0, 0, 0, 0, 0};
+  int64_t launches[MMG_T_COUNT] = {0, 0, 0, 0, 0};
+  int64_t bytes[MMG_T_COUNT] = {0, 0, 0, 0, 0};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+  std::vector<cudaEvent_t> pool;
+  int64_t total_launches = 0;
+};
+
+struct Grid {
+  int device = 0;
+  int n = 0;        // laplaceMatSize_
+  int A = 0;        // rows of laplaceMat_ (n, or n+1 with any Neumann boundary)
+  bool neumann = false, implicit = false;
+  mmg_props props{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Timers* timers = nullptr;   // shared with the owning solver (or own)
+  Timers own_timers;
+
+  // host mirrors of the small / integer state
+  std::vector<double> hx, hy, hnx, hny;
+  std::vector<int> bcflags;
+  std::vector<Boundary> boundaries;
+  std::vector<int> order;      // rcm permutation (new -> old)
+  std::vector<double> diags;   // Grid::diags
+  HostCsr nbc;                 // neumann_boundary_coeffs_ (only rows near Neumann boundaries are non-empty)
+  bool have_laplacian = false;
+
+  // device state
+  DevBuf<double> x, x_alt, b, r;         // values_, sweep scratch, source_, residual scratch (A entries)
+  DevBuf<double> px, py;                 // points_
+  DevBuf<unsigned char> rowflag;         // bcFlags_ per row as uint8 (A entries; regularisation row = 0)
+  DevBuf<int> dir_pts, neu_pts;          // Dirichlet / Neumann node lists in boundary-list order
+  DevBuf<double> dir_vals, neu_vals;
+  HybMatrix Lap;                         // laplaceMat_
+  DevBuf<double> partials;               // reduction scratch
+  DevBuf<int> abort_flag;
+  // multicolour schedule
+  bool have_colours = false;
+  int n_colours = 0;
+  std::vector<int> colour_ptr;           // n_colours+1
+  DevBuf<int> colour_rows;               // rows grouped by colour, ascending inside a colour
+  std::vector<int> colour_host;          // per-row colour (-1 skipped)
+  // per-level assembly state (device kNN lists etc.) lives in assembly.cu
+  void* asm_state = nullptr;
+
+  ~Grid();
+  void sync() { MMG_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+struct Solver {
+  int flavour = MMG_FLAVOUR_MULTIGRID;
+  int smoother = MMG_SMOOTHER_LEXICOGRAPHIC;
+  std::vector<Grid*> grids;                 // sorted ascending by (size, pointer), like multigrid.cpp:116-122
+  std::vector<HybMatrix*> restrict_, prolong_;  // [i] as in the reference (restrict_[0]==nullptr, prolong_.back()==nullptr)
+  DevBuf<double> hist;                      // residuals_ on device
+  int hist_len = 0;
+  std::vector<double> hist_host;
+  cudaStream_t stream = nullptr;
+  Timers timers;
+  ~Solver();
+};
+
+// ---- operations (kernels.cu) -------------------------------------------------------------------
+void op_residual(Grid& g, double* r_out);                        // r = b - A x, Dirichlet rows zeroed (device ptr, A entries)
+void op_residual_norm(Grid& g, double* ratio_dev);               // *ratio_dev = |b-Ax|_1 / |b|_1
+void op_sor(Grid& g, int smoother);                              // props.iters sweeps + bound_eval_neumann after each
+void op_bound_eval_neumann(Grid& g);
+void op_boundary_op(Grid& g, int coarse);
+void op_modify_coeff_neumann(Grid& g, int coarse);
+void op_fix_vector_bound_coarse(Grid& g, double* vec_dev);
+void op_zero_values(Grid& g);
+// coarse.b[0:Nc] = R * fine_residual[0:Nf]; then the masks of multigrid.cpp:82-86
+void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fine_res_dev);
+// fine.x[0:Nf] += P * coarse.x[0:Nc] (Dirichlet rows masked when the fine grid is not Neumann) multigrid.cpp:102-106
+void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P);
+void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class);
+void build_colouring(Grid& g);
+void compute_lex_levels(Grid& g, std::vector<int>& level, int& n_levels);
+
+// ---- assembly (assembly.cu) ---------------------------------------------------------------------
+void asm_release(Grid& g);
+void asm_knn_points(Grid& g, int m, const double* qx, const double* qy, const int* qflag, int neumann, int k, int* out_host);
+void asm_rcm_order_points(Grid& g);
+void asm_build_deriv_normal_bound(Grid& g);
+void asm_build_laplacian(Grid& g);
+void asm_weights(Grid& g, int which, int m, const int* ids, double* w, int* nb);
+void asm_point_interp_weights(Grid& g, int m, const double* px, const double* py, int polyDeg, double* w, int* nb);
+void asm_build_interp(Grid& base, Grid& target, int polyDeg, HybMatrix& out);
+
+// ---- timers ---------------------------------------------------------------------------------------
+struct TimedScope {
+  Timers* t; int cls; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  TimedScope(Timers* t_, int cls_, cudaStream_t s_, int64_t bytes, int launches = 1);
+  ~TimedScope();
+};
+void timers_collect(Timers& t);
+
+}  // namespace mmg

@@ -1,0 +1,809 @@
+// Solve-path kernels (sm_100a): residual / interpolation SpMV over the row-chunk HYB layout,
+// lexicographic SOR as a dependency-DAG sweep (value-carried ready flags in L2), multicolour SOR,
+// Neumann boundary evaluation, the regularisation-row reductions and the small scatter ops.
+//
+// Reference semantics restated by each kernel are cited inline (paths relative to
+// /root/reference/MeshlessPoisson/).  All arithmetic is fp64; multiplications and additions of the
+// row sums are issued as separate roundings (__dmul_rn/__dadd_rn) because the reference is built
+// without FMA contraction.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "mmg_internal.hpp"
+
+namespace mmg {
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr unsigned long long kSentinelBits = 0xFFF8DEADBEEF0001ull;  // quiet NaN with a payload no computation produces
+
+enum { OP_SPMV = 0, OP_RESID = 1, OP_PROLONG = 2, OP_RESTRICT = 3 };
+
+__device__ __forceinline__ const double* row_val(const HybView& A, int r) {
+  return reinterpret_cast<const double*>(A.chunks + (size_t)r * A.chunk_bytes);
+}
+__device__ __forceinline__ const int* row_col(const HybView& A, int r) {
+  return reinterpret_cast<const int*>(A.chunks + (size_t)r * A.chunk_bytes + (size_t)A.W * 8);
+}
+__device__ __forceinline__ int ovf_find(const HybView& A, int row) {  // index into ovf_rows, rows with len>W only
+  int lo = 0, hi = A.n_ovf - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (A.ovf_rows[mid] < row) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+template <int LPR>
+__device__ __forceinline__ double group_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(mask, v, o));
+  return v;
+}
+template <int LPR>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  if (LPR == 32) return 0xffffffffu;
+  return ((1u << LPR) - 1u) << ((lane / LPR) * LPR);
+}
+__device__ __forceinline__ double ld_relaxed(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool is_sentinel(double v) { return (unsigned long long)__double_as_longlong(v) == kSentinelBits; }
+
+// block-wide sum of two doubles; result valid in thread 0
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double sa[kBlock / 32], sb[kBlock / 32];
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    a = l < (blockDim.x >> 5) ? sa[l] : 0.0;
+    b = l < (blockDim.x >> 5) ? sb[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = op(A, x): one LPR-lane group per row, lanes stride over the row chunk.
+//   OP_SPMV      y = A x                                  (Eigen sparse*dense, grid.cpp:148, multigrid.cpp:81,102)
+//   OP_RESID     y = b - A x, Dirichlet rows -> 0          (Grid::residual grid.cpp:147-151); optional |.|_1 partials
+//   OP_PROLONG   y += A x except masked Dirichlet rows     (multigrid.cpp:102-106)
+//   OP_RESTRICT  y = A x, Dirichlet rows -> 0, Neumann rows -> 0 when mask_neumann (multigrid.cpp:81-86)
+// ------------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(kBlock) k_spmv(HybView A, const double* __restrict__ x, const double* __restrict__ b, double* y,
+                                                 const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
+                                                 double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;  // groups per warp
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double num = 0.0, den = 0.0;
+  for (int row0 = warp * GPW; row0 < A.rows; row0 += nwarps * GPW) {
+    const int row = row0 + lane / LPR;
+    const bool valid = row < A.rows;
+    double acc = 0.0;
+    if (valid) {
+      const int len = A.len[row];
+      const double* __restrict__ v = row_val(A, row);
+      const int* __restrict__ c = row_col(A, row);
+      const int m = len < A.W ? len : A.W;
+      for (int k = gl; k < m; k += LPR) acc = __dadd_rn(acc, __dmul_rn(v[k], __ldg(x + c[k])));
+      if (len > A.W) {
+        const int o = ovf_find(A, row);
+        for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) acc = __dadd_rn(acc, __dmul_rn(A.ovf_val[k], __ldg(x + A.ovf_col[k])));
+      }
+    }
+    acc = group_sum<LPR>(acc, gmask);
+    if (valid && gl == 0) {
+      const int flag = rowflag ? rowflag[row] : 0;
+      if (op == OP_SPMV) {
+        y[row] = acc;
+      } else if (op == OP_RESID) {
+        const double bi = b[row];
+        double t = __dsub_rn(bi, acc);
+        if (flag == 1) t = 0.0;
+        if (y) y[row] = t;
+        num += fabs(t);
+        den += fabs(bi);
+      } else if (op == OP_PROLONG) {
+        if (!(mask_dirichlet && flag == 1)) y[row] = __dadd_rn(y[row], acc);
+      } else {  // OP_RESTRICT
+        double t = acc;
+        if (flag == 1) t = 0.0;
+        if (mask_neumann && flag == 2) t = 0.0;
+        y[row] = t;
+      }
+    }
+  }
+  if (partial) {
+    block_sum2(num, den);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = num; partial[2 * blockIdx.x + 1] = den; }
+  }
+}
+
+// partial sums of the regularisation row's off-diagonal dot product: sum_j val[j]*x[col[j]] (grid.cpp:570-576)
+__global__ void __launch_bounds__(kBlock) k_regdot(const int* __restrict__ col, const double* __restrict__ val, int len, const double* x,
+                                                   double* __restrict__ partial) {
+  double s = 0.0, dummy = 0.0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) s += val[j] * x[col[j]];
+  block_sum2(s, dummy);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// single block: fold norm partials (+ regularisation row) into r[N] and *ratio = |r|_1/|b|_1 (multigrid.cpp:112-115)
+__global__ void __launch_bounds__(kBlock) k_finish_residual(const double* __restrict__ norm_partial, int n_norm, const double* __restrict__ reg_partial,
+                                                            int n_reg, int reg_row, double reg_diag, const double* __restrict__ x,
+                                                            const double* __restrict__ b, double* r, double* ratio) {
+  double num = 0.0, den = 0.0;
+  for (int i = threadIdx.x; i < n_norm; i += blockDim.x) { num += norm_partial[2 * i]; den += norm_partial[2 * i + 1]; }
+  block_sum2(num, den);
+  __syncthreads();
+  double dot = 0.0, dummy = 0.0;
+  if (reg_row >= 0) {
+    for (int i = threadIdx.x; i < n_reg; i += blockDim.x) dot += reg_partial[i];
+    block_sum2(dot, dummy);
+  }
+  if (threadIdx.x == 0) {
+    if (reg_row >= 0) {
+      const double t = b[reg_row] - (dot + reg_diag * x[reg_row]);
+      if (r) r[reg_row] = t;
+      num += fabs(t);
+      den += fabs(b[reg_row]);
+    }
+    if (ratio) *ratio = num / den;
+  }
+}
+
+// single block: SOR update of the regularisation row (it is the last row of the sweep, grid.cpp:117-143)
+__global__ void __launch_bounds__(kBlock) k_finish_sor_reg(const double* __restrict__ reg_partial, int n_reg, int reg_row, double reg_diag, double omega,
+                                                           const double* __restrict__ b, const double* x_old, double* x_new) {
+  double dot = 0.0, dummy = 0.0;
+  for (int i = threadIdx.x; i < n_reg; i += blockDim.x) dot += reg_partial[i];
+  block_sum2(dot, dummy);
+  if (threadIdx.x == 0) {
+    double xi = -dot;
+    xi += b[reg_row];
+    xi *= omega / reg_diag;
+    xi += (1 - omega) * x_old[reg_row];
+    x_new[reg_row] = xi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lexicographic SOR sweep (Grid::sor grid.cpp:117-143) as a dependency-DAG sweep.
+// x_new is pre-filled by k_sweep_init: rows the sweep skips carry their old value, rows it visits
+// carry a sentinel.  Row i reads x_new[c] for c<i (spinning while it is the sentinel) and x_old[c]
+// for c>i, so the result is the sequential in-place sweep.  Groups take rows round-robin in
+// increasing order and the launch is cooperative (all CTAs resident), hence the lowest unfinished
+// row always has a running owner whose dependencies are done: no deadlock.  A clock64 watchdog
+// turns any stall into MMG_ERR_TIMEOUT instead of a hung GPU.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int T>
+__global__ void __launch_bounds__(kBlock) k_sor_lex(HybView A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b,
+                                                    const double* __restrict__ x_old, double* x_new, double omega, int* abort_flag,
+                                                    long long timeout_cycles) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long t_start = clock64();
+  for (int row0 = warp * GPW; row0 < A.rows; row0 += nwarps * GPW) {
+    const int row = row0 + lane / LPR;
+    const bool valid = row < A.rows && rowflag[row] == 0;
+    double acc = 0.0, diag = 0.0;
+    double pv[T];
+    int pc[T];
+    unsigned pend = 0;
+    if (valid) {
+      const int len = A.len[row];
+      const double* __restrict__ v = row_val(A, row);
+      const int* __restrict__ c = row_col(A, row);
+      const int m = len < A.W ? len : A.W;
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        const int k = gl + t * LPR;
+        pv[t] = 0.0; pc[t] = 0;
+        if (k < m) {
+          const double a = v[k];
+          const int col = c[k];
+          if (k == 0) diag = a;                                   // diag-first layout
+          else if (col > row) acc = __dsub_rn(acc, __dmul_rn(a, __ldg(x_old + col)));
+          else { pv[t] = a; pc[t] = col; pend |= 1u << t; }
+        }
+      }
+      if (len > A.W) {  // rare spill rows (implicit Neumann fill-in): blocking per-entry wait
+        const int o = ovf_find(A, row);
+        for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) {
+          const int col = A.ovf_col[k];
+          double xv;
+          if (col > row) xv = __ldg(x_old + col);
+          else {
+            xv = ld_relaxed(x_new + col);
+            while (is_sentinel(xv)) {
+              if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); xv = 0.0; break; }
+              xv = ld_relaxed(x_new + col);
+            }
+          }
+          acc = __dsub_rn(acc, __dmul_rn(A.ovf_val[k], xv));
+        }
+      }
+    }
+    bool finished = !valid;
+    unsigned spins = 0;
+    while (true) {
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        if (pend & (1u << t)) {
+          const double xv = ld_relaxed(x_new + pc[t]);
+          if (!is_sentinel(xv)) { acc = __dsub_rn(acc, __dmul_rn(pv[t], xv)); pend &= ~(1u << t); }
+        }
+      }
+      const unsigned ball = __ballot_sync(0xffffffffu, pend != 0);
+      if (!finished && (ball & gmask) == 0) {
+        const double s = group_sum<LPR>(acc, gmask);
+        if (gl == 0) {                                          // x=sum; x+=b; x*=w/d; x+=(1-w)x_old (grid.cpp:137-141)
+          double xi = __dadd_rn(s, b[row]);
+          xi = __dmul_rn(xi, omega / diag);
+          xi = __dadd_rn(xi, __dmul_rn(1 - omega, x_old[row]));
+          st_relaxed(x_new + row, xi);
+        }
+        finished = true;
+      }
+      if (__all_sync(0xffffffffu, finished)) break;
+      if ((++spins & 0xff) == 0) {
+        if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) {
+          atomicExch(abort_flag, 1);
+          if (!finished && gl == 0) st_relaxed(x_new + row, 0.0);  // unblock everyone behind us
+          return;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_sweep_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x_old, double* x_new,
+                                                       int rows, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) x_new[i] = rowflag[i] != 0 ? x_old[i] : __longlong_as_double((long long)kSentinelBits);
+  else if (i < total) x_new[i] = x_old[i];
+}
+
+// Multicolour SOR phase: all rows of one colour, in place (same row update as grid.cpp:122-141).
+template <int LPR>
+__global__ void __launch_bounds__(kBlock) k_sor_mc(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
+                                                   double omega) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i0 = warp * GPW; i0 < count; i0 += nwarps * GPW) {
+    const int i = i0 + lane / LPR;
+    const bool valid = i < count;
+    double acc = 0.0, diag = 0.0;
+    int row = 0;
+    if (valid) {
+      row = rows_list[i];
+      const int len = A.len[row];
+      const double* __restrict__ v = row_val(A, row);
+      const int* __restrict__ c = row_col(A, row);
+      const int m = len < A.W ? len : A.W;
+      for (int k = gl; k < m; k += LPR) {
+        const double a = v[k];
+        if (k == 0) diag = a;
+        else acc = __dsub_rn(acc, __dmul_rn(a, x[c[k]]));
+      }
+      if (len > A.W) {
+        const int o = ovf_find(A, row);
+        for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) acc = __dsub_rn(acc, __dmul_rn(A.ovf_val[k], x[A.ovf_col[k]]));
+      }
+    }
+    acc = group_sum<LPR>(acc, gmask);
+    if (valid && gl == 0) {
+      double xi = __dadd_rn(acc, b[row]);
+      xi = __dmul_rn(xi, omega / diag);
+      xi = __dadd_rn(xi, __dmul_rn(1 - omega, x[row]));
+      x[row] = xi;
+    }
+  }
+}
+
+// Grid::bound_eval_neumann grid.cpp:73-103: x_c = (b_c - sum_{k!=c} a_ck x_k)/a_cc for every Neumann node.
+// Neumann rows reference only interior nodes and themselves (kNN exclusion rule grid.cpp:236,244; checked at
+// upload), so the list can be evaluated in parallel.
+template <int LPR>
+__global__ void __launch_bounds__(kBlock) k_bound_eval(HybView A, const int* __restrict__ nodes, int count, const double* __restrict__ b, double* x) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i0 = warp * GPW; i0 < count; i0 += nwarps * GPW) {
+    const int i = i0 + lane / LPR;
+    const bool valid = i < count;
+    double acc = 0.0, diag = 0.0;
+    int row = 0;
+    if (valid) {
+      row = nodes[i];
+      const int len = A.len[row];
+      const double* __restrict__ v = row_val(A, row);
+      const int* __restrict__ c = row_col(A, row);
+      const int m = len < A.W ? len : A.W;
+      for (int k = gl; k < m; k += LPR) {
+        const double a = v[k];
+        if (k == 0) diag = a;
+        else acc = __dsub_rn(acc, __dmul_rn(x[c[k]], a));
+      }
+      if (len > A.W) {
+        const int o = ovf_find(A, row);
+        for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) acc = __dsub_rn(acc, __dmul_rn(x[A.ovf_col[k]], A.ovf_val[k]));
+      }
+    }
+    acc = group_sum<LPR>(acc, gmask);
+    if (valid && gl == 0) x[row] = __dadd_rn(b[row], acc) / diag;
+  }
+}
+
+__global__ void k_scatter(const int* __restrict__ idx, const double* __restrict__ vals, int count, double* dst, int use_zero) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[idx[i]] = use_zero ? 0.0 : vals[i];
+}
+__global__ void k_set_one(double* dst, int i, double v) { dst[i] = v; }
+
+int lanes_for_width(int W) { return W >= 48 ? 32 : (W >= 24 ? 16 : 8); }
+
+int grid_for(int work_groups_rows, int lpr, int sm_count) {
+  // rows -> warps -> blocks; cap at a few waves of resident CTAs (persistent grid-stride beyond that)
+  const int gpw = 32 / lpr;
+  const long long warps = ((long long)work_groups_rows + gpw - 1) / gpw;
+  long long blocks = (warps * 32 + kBlock - 1) / kBlock;
+  const long long cap = (long long)sm_count * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int sm_count_of(int device) {
+  static int cached[64] = {0};
+  if (device < 64 && cached[device]) return cached[device];
+  int n = 0;
+  MMG_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  if (device < 64) cached[device] = n;
+  return n;
+}
+
+void ensure_partials(Grid& g, size_t n) {
+  if (g.partials.n < n) g.partials.alloc(n);
+}
+
+template <class F>
+void dispatch_lpr(int W, F&& f) {
+  const int lpr = lanes_for_width(W);
+  if (lpr == 32) f(std::integral_constant<int, 32>());
+  else if (lpr == 16) f(std::integral_constant<int, 16>());
+  else f(std::integral_constant<int, 8>());
+}
+
+void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
+                 double* partial, int* nblocks_out, int device, cudaStream_t s) {
+  const int sms = sm_count_of(device);
+  dispatch_lpr(M.W, [&](auto L) {
+    constexpr int LPR = decltype(L)::value;
+    const int blocks = grid_for(M.rows, LPR, sms);
+    if (nblocks_out) *nblocks_out = blocks;
+    k_spmv<LPR><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial);
+  });
+  MMG_CUDA(cudaGetLastError());
+}
+
+constexpr int kRegBlocks = 296;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// timers
+// ------------------------------------------------------------------------------------------------
+TimedScope::TimedScope(Timers* t_, int cls_, cudaStream_t s_, int64_t bytes, int launches) : t(t_), cls(cls_), s(s_) {
+  if (!t) return;
+  t->total_launches += launches;
+  t->launches[cls] += launches;
+  t->bytes[cls] += bytes;
+  if (!t->on) return;
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!t->pool.empty()) { e = t->pool.back(); t->pool.pop_back(); }
+    else MMG_CUDA(cudaEventCreate(&e));
+    return e;
+  };
+  e0 = get(); e1 = get();
+  MMG_CUDA(cudaEventRecord(e0, s));
+}
+TimedScope::~TimedScope() {
+  if (!t || !t->on || !e0) return;
+  cudaEventRecord(e1, s);
+  t->pending.push_back({cls, {e0, e1}});
+}
+void timers_collect(Timers& t) {
+  for (auto& p : t.pending) {
+    float ms = 0;
+    cudaEventSynchronize(p.second.second);
+    cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+    t.ms[p.first] += ms;
+    t.pool.push_back(p.second.first);
+    t.pool.push_back(p.second.second);
+  }
+  t.pending.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// host CSR <-> device HYB
+// ------------------------------------------------------------------------------------------------
+void hyb_from_csr(HybMatrix& M, const HostCsr& A, bool diag_first, bool has_reg, cudaStream_t s) {
+  const int R = has_reg ? A.rows - 1 : A.rows;
+  M.rows = R; M.cols = A.cols; M.diag_first = diag_first; M.nnz = A.nnz();
+  std::vector<int> len(R);
+  int maxlen = 0;
+  for (int r = 0; r < R; r++) { len[r] = A.ptr[r + 1] - A.ptr[r]; maxlen = std::max(maxlen, len[r]); }
+  int W = maxlen;
+  if (R > 0) {
+    std::vector<int> sorted(len);
+    std::nth_element(sorted.begin(), sorted.begin() + R / 2, sorted.end());
+    const int med = sorted[R / 2];
+    if (maxlen > med + med / 4) {  // a few long rows (implicit-Neumann fill-in): spill them instead of padding every row
+      const size_t q = (size_t)(0.985 * (R - 1));
+      std::nth_element(sorted.begin(), sorted.begin() + q, sorted.end());
+      W = std::max(sorted[q], med);
+    }
+  }
+  if (W < 1) W = 1;
+  M.W = W;
+  M.chunk_bytes = ((size_t)W * 12 + 31) / 32 * 32;
+  std::vector<unsigned char> chunks((size_t)R * M.chunk_bytes, 0);
+  std::vector<int> ovf_rows, ovf_ptr(1, 0), ovf_col;
+  std::vector<double> ovf_val;
+  std::vector<std::pair<int, double>> row;
+  for (int r = 0; r < R; r++) {
+    row.clear();
+    int dpos = -1;
+    for (int k = A.ptr[r]; k < A.ptr[r + 1]; k++) {
+      if (diag_first && A.idx[k] == r && dpos < 0) dpos = (int)row.size();
+      row.push_back({A.idx[k], A.val[k]});
+    }
+    if (diag_first) {
+      MMG_REQUIRE(dpos >= 0 || len[r] == 0, MMG_ERR_ARG, "row " + std::to_string(r) + " of the Laplacian has no diagonal entry");
+      if (dpos > 0) std::rotate(row.begin(), row.begin() + dpos, row.begin() + dpos + 1);
+    }
+    double* v = reinterpret_cast<double*>(chunks.data() + (size_t)r * M.chunk_bytes);
+    int* c = reinterpret_cast<int*>(chunks.data() + (size_t)r * M.chunk_bytes + (size_t)W * 8);
+    const int m = std::min(len[r], W);
+    for (int k = 0; k < m; k++) { v[k] = row[k].second; c[k] = row[k].first; }
+    for (int k = m; k < W; k++) { v[k] = 0.0; c[k] = r < A.cols ? r : 0; }
+    if (len[r] > W) {
+      ovf_rows.push_back(r);
+      for (int k = W; k < len[r]; k++) { ovf_col.push_back(row[k].first); ovf_val.push_back(row[k].second); }
+      ovf_ptr.push_back((int)ovf_col.size());
+    }
+  }
+  M.chunks.upload(chunks, s);
+  M.len.upload(len, s);
+  M.n_ovf = (int)ovf_rows.size();
+  if (M.n_ovf) {
+    M.ovf_rows.upload(ovf_rows, s); M.ovf_ptr.upload(ovf_ptr, s); M.ovf_col.upload(ovf_col, s); M.ovf_val.upload(ovf_val, s);
+  }
+  M.reg_row = -1; M.reg_len = 0;
+  if (has_reg) {
+    const int r = A.rows - 1;
+    std::vector<int> rc; std::vector<double> rv;
+    M.reg_diag = 0;
+    for (int k = A.ptr[r]; k < A.ptr[r + 1]; k++) {
+      if (A.idx[k] == r) M.reg_diag = A.val[k];
+      else { rc.push_back(A.idx[k]); rv.push_back(A.val[k]); }
+    }
+    M.reg_row = r; M.reg_len = (int)rc.size();
+    M.reg_col.upload(rc, s); M.reg_val.upload(rv, s);
+  }
+  MMG_CUDA(cudaStreamSynchronize(s));  // host staging buffers die here
+}
+
+void hyb_to_csr(const HybMatrix& M, HostCsr& A, cudaStream_t s) {
+  const int R = M.rows;
+  std::vector<unsigned char> chunks = M.chunks.to_host(s);
+  std::vector<int> len = M.len.to_host(s);
+  std::vector<int> ovf_rows, ovf_ptr, ovf_col; std::vector<double> ovf_val;
+  if (M.n_ovf) { ovf_rows = M.ovf_rows.to_host(s); ovf_ptr = M.ovf_ptr.to_host(s); ovf_col = M.ovf_col.to_host(s); ovf_val = M.ovf_val.to_host(s); }
+  A.rows = R + (M.reg_row >= 0 ? 1 : 0); A.cols = M.cols;
+  A.ptr.assign(A.rows + 1, 0); A.idx.clear(); A.val.clear();
+  std::vector<std::pair<int, double>> row;
+  size_t o = 0;
+  for (int r = 0; r < R; r++) {
+    row.clear();
+    const double* v = reinterpret_cast<const double*>(chunks.data() + (size_t)r * M.chunk_bytes);
+    const int* c = reinterpret_cast<const int*>(chunks.data() + (size_t)r * M.chunk_bytes + (size_t)M.W * 8);
+    const int m = std::min(len[r], M.W);
+    for (int k = 0; k < m; k++) row.push_back({c[k], v[k]});
+    if (len[r] > M.W) {
+      for (int k = ovf_ptr[o]; k < ovf_ptr[o + 1]; k++) row.push_back({ovf_col[k], ovf_val[k]});
+      o++;
+    }
+    if (M.diag_first && !row.empty()) {  // put the diagonal back in column order
+      auto d = row.front();
+      row.erase(row.begin());
+      auto it = std::lower_bound(row.begin(), row.end(), d, [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+      row.insert(it, d);
+    }
+    for (auto& e : row) { A.idx.push_back(e.first); A.val.push_back(e.second); }
+    A.ptr[r + 1] = (int)A.idx.size();
+  }
+  if (M.reg_row >= 0) {
+    std::vector<int> rc = M.reg_col.to_host(s); std::vector<double> rv = M.reg_val.to_host(s);
+    bool placed = false;
+    for (size_t k = 0; k < rc.size(); k++) {
+      if (!placed && rc[k] > M.reg_row) { A.idx.push_back(M.reg_row); A.val.push_back(M.reg_diag); placed = true; }
+      A.idx.push_back(rc[k]); A.val.push_back(rv[k]);
+    }
+    if (!placed) { A.idx.push_back(M.reg_row); A.val.push_back(M.reg_diag); }
+    A.ptr[R + 1] = (int)A.idx.size();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operations
+// ------------------------------------------------------------------------------------------------
+static void residual_impl(Grid& g, double* r_out, double* ratio_dev) {
+  const HybMatrix& L = g.Lap;
+  MMG_REQUIRE(g.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+  const int sms = sm_count_of(g.device);
+  const int maxblocks = sms * 32 + 8;
+  ensure_partials(g, (size_t)2 * maxblocks + kRegBlocks);
+  double* norm_partial = g.partials.p;
+  double* reg_partial = g.partials.p + 2 * maxblocks;
+  int nb = 0;
+  {
+    TimedScope ts(g.timers, MMG_T_RESIDUAL, g.stream, L.matrix_bytes() + (int64_t)g.A * 24, 2 + (L.reg_row >= 0));
+    launch_spmv(L, g.x.p, g.b.p, r_out, g.rowflag.p, OP_RESID, 0, 0, norm_partial, &nb, g.device, g.stream);
+    if (L.reg_row >= 0) {
+      k_regdot<<<kRegBlocks, kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, g.x.p, reg_partial);
+      MMG_CUDA(cudaGetLastError());
+    }
+    k_finish_residual<<<1, kBlock, 0, g.stream>>>(norm_partial, nb, reg_partial, kRegBlocks, L.reg_row, L.reg_diag, g.x.p, g.b.p, r_out, ratio_dev);
+    MMG_CUDA(cudaGetLastError());
+  }
+}
+
+void op_residual(Grid& g, double* r_out) { residual_impl(g, r_out, nullptr); }
+void op_residual_norm(Grid& g, double* ratio_dev) { residual_impl(g, nullptr, ratio_dev); }
+
+void op_bound_eval_neumann(Grid& g) {
+  if (g.neu_pts.n == 0) return;
+  MMG_REQUIRE(g.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+  const int sms = sm_count_of(g.device);
+  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.neu_pts.n * (12 * g.Lap.W + 24));
+  dispatch_lpr(g.Lap.W, [&](auto Lc) {
+    constexpr int LPR = decltype(Lc)::value;
+    k_bound_eval<LPR><<<grid_for((int)g.neu_pts.n, LPR, sms), kBlock, 0, g.stream>>>(g.Lap.view(), g.neu_pts.p, (int)g.neu_pts.n, g.b.p, g.x.p);
+  });
+  MMG_CUDA(cudaGetLastError());
+}
+
+void op_boundary_op(Grid& g, int coarse) {  // grid.cpp:42-51
+  if (g.dir_pts.n == 0) return;
+  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.dir_pts.n * 20);
+  k_scatter<<<((int)g.dir_pts.n + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.dir_pts.p, g.dir_vals.p, (int)g.dir_pts.n, g.x.p, coarse);
+  MMG_CUDA(cudaGetLastError());
+}
+
+void op_modify_coeff_neumann(Grid& g, int coarse) {  // grid.cpp:62-72
+  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.neu_pts.n * 20 + 8, 1 + (g.neu_pts.n ? 1 : 0));
+  if (g.neu_pts.n) k_scatter<<<((int)g.neu_pts.n + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.neu_pts.p, g.neu_vals.p, (int)g.neu_pts.n, g.b.p, coarse);
+  k_set_one<<<1, 1, 0, g.stream>>>(g.b.p, (int)g.b.n - 1, 0.0);
+  MMG_CUDA(cudaGetLastError());
+}
+
+void op_fix_vector_bound_coarse(Grid& g, double* vec_dev) {  // grid.cpp:197-205
+  if (g.dir_pts.n == 0) return;
+  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.dir_pts.n * 12);
+  k_scatter<<<((int)g.dir_pts.n + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.dir_pts.p, nullptr, (int)g.dir_pts.n, vec_dev, 1);
+  MMG_CUDA(cudaGetLastError());
+}
+
+void op_zero_values(Grid& g) {
+  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.A * 8);
+  g.x.zero(g.stream);
+}
+
+void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class) {
+  TimedScope ts(ctx.timers, timer_class, ctx.stream, M.matrix_bytes() + (int64_t)M.rows * 8 + (int64_t)M.cols * 8);
+  launch_spmv(M, x_dev, nullptr, y_dev, nullptr, OP_SPMV, 0, 0, nullptr, nullptr, ctx.device, ctx.stream);
+}
+
+void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fine_res_dev) {
+  MMG_REQUIRE(R.rows == coarse.n && R.cols == fine.n, MMG_ERR_STATE, "restriction matrix shape does not match the grids");
+  {
+    TimedScope ts(fine.timers, MMG_T_RESTRICT, fine.stream, R.matrix_bytes() + (int64_t)coarse.n * 8 + (int64_t)fine.n * 8);
+    // fix_vector_bound_coarse on the coarse source and, if the FINE grid is Neumann, modify_coeff_neumann("coarse"):
+    // both are masks on the output rows (multigrid.cpp:82-86)
+    launch_spmv(R, fine_res_dev, nullptr, coarse.b.p, coarse.rowflag.p, OP_RESTRICT, 1, fine.neumann ? 1 : 0, nullptr, nullptr, fine.device, fine.stream);
+  }
+  if (fine.neumann) {  // source_(rows-1)=0 (multigrid.cpp:84) and the same store inside modify_coeff_neumann (grid.cpp:71)
+    TimedScope ts(fine.timers, MMG_T_OTHER, fine.stream, 8);
+    k_set_one<<<1, 1, 0, fine.stream>>>(coarse.b.p, (int)coarse.b.n - 1, 0.0);
+    MMG_CUDA(cudaGetLastError());
+  }
+}
+
+void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P) {
+  MMG_REQUIRE(P.rows == fine.n && P.cols == coarse.n, MMG_ERR_STATE, "prolongation matrix shape does not match the grids");
+  TimedScope ts(fine.timers, MMG_T_PROLONG, fine.stream, P.matrix_bytes() + (int64_t)fine.n * 16 + (int64_t)coarse.n * 8);
+  launch_spmv(P, coarse.x.p, nullptr, fine.x.p, fine.rowflag.p, OP_PROLONG, fine.neumann ? 0 : 1, 0, nullptr, nullptr, fine.device, fine.stream);
+}
+
+// ---- SOR -----------------------------------------------------------------------------------------
+template <int LPR, int T>
+static void launch_lex(Grid& g, const double* x_old, double* x_new) {
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_lex<LPR, T>, kBlock, 0));
+  const int sms = sm_count_of(g.device);
+  int blocks = blocks_per_sm * sms;
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("MMG_LEX_BLOCKS"); cap = e ? atoi(e) : 0; }
+  if (cap > 0 && blocks > cap) blocks = cap;
+  const int need = grid_for(g.Lap.rows, LPR, 1 << 20);
+  if (blocks > need) blocks = need;
+  HybView A = g.Lap.view();
+  const unsigned char* rf = g.rowflag.p;
+  const double* b = g.b.p;
+  double omega = g.props.omega;
+  int* abortp = g.abort_flag.p;
+  long long timeout = 6000000000ll;  // ~3 s of SM clocks
+  void* args[] = {&A, &rf, &b, &x_old, &x_new, &omega, &abortp, &timeout};
+  MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_lex<LPR, T>, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+}
+
+static void sor_lex_sweep(Grid& g) {
+  const HybMatrix& L = g.Lap;
+  const int W = L.W;
+  const int lpr = lanes_for_width(W);
+  const int T = (W + lpr - 1) / lpr;
+  const double* x_old = g.x.p;
+  double* x_new = g.x_alt.p;
+  k_sweep_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, x_old, x_new, L.rows, g.A);
+  MMG_CUDA(cudaGetLastError());
+#define LEX_CASE(LPR_, T_) if (lpr == LPR_ && T <= T_) { launch_lex<LPR_, T_>(g, x_old, x_new); } else
+  LEX_CASE(32, 1) LEX_CASE(32, 2) LEX_CASE(32, 3) LEX_CASE(32, 4) LEX_CASE(32, 6) LEX_CASE(32, 8)
+  LEX_CASE(16, 2) LEX_CASE(16, 3)
+  LEX_CASE(8, 1) LEX_CASE(8, 2) LEX_CASE(8, 3)
+  { throw Error(MMG_ERR_ARG, "stencil width " + std::to_string(W) + " is outside the lexicographic kernel's dispatch table"); }
+#undef LEX_CASE
+  if (L.reg_row >= 0) {
+    double* reg_partial = g.partials.p;
+    k_regdot<<<kRegBlocks, kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, x_new, reg_partial);
+    k_finish_sor_reg<<<1, kBlock, 0, g.stream>>>(reg_partial, kRegBlocks, L.reg_row, L.reg_diag, g.props.omega, g.b.p, x_old, x_new);
+    MMG_CUDA(cudaGetLastError());
+  }
+  std::swap(g.x.p, g.x_alt.p);
+}
+
+static void sor_mc_sweep(Grid& g) {
+  const HybMatrix& L = g.Lap;
+  const int sms = sm_count_of(g.device);
+  const int ncol_rows = L.reg_row >= 0 ? g.n_colours - 1 : g.n_colours;  // the regularisation row is the last colour
+  dispatch_lpr(L.W, [&](auto Lc) {
+    constexpr int LPR = decltype(Lc)::value;
+    for (int c = 0; c < ncol_rows; c++) {
+      const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
+      if (count == 0) continue;
+      k_sor_mc<LPR><<<grid_for(count, LPR, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
+    }
+  });
+  MMG_CUDA(cudaGetLastError());
+  if (L.reg_row >= 0) {
+    double* reg_partial = g.partials.p;
+    k_regdot<<<kRegBlocks, kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, g.x.p, reg_partial);
+    k_finish_sor_reg<<<1, kBlock, 0, g.stream>>>(reg_partial, kRegBlocks, L.reg_row, L.reg_diag, g.props.omega, g.b.p, g.x.p, g.x.p);
+    MMG_CUDA(cudaGetLastError());
+  }
+}
+
+void op_sor(Grid& g, int smoother) {
+  MMG_REQUIRE(g.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+  const HybMatrix& L = g.Lap;
+  ensure_partials(g, (size_t)kRegBlocks + 2 * (sm_count_of(g.device) * 32 + 8));
+  if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.have_colours) build_colouring(g);
+  for (int it = 0; it < g.props.iters; it++) {
+    {
+      const int launches = smoother == MMG_SMOOTHER_MULTICOLOUR ? g.n_colours + 1 : 2 + (L.reg_row >= 0 ? 2 : 0);
+      TimedScope ts(g.timers, MMG_T_SOR, g.stream, L.matrix_bytes() + (int64_t)g.A * 28, launches);
+      if (smoother == MMG_SMOOTHER_MULTICOLOUR) sor_mc_sweep(g); else sor_lex_sweep(g);
+    }
+    op_bound_eval_neumann(g);  // grid.cpp:144
+  }
+}
+
+// ---- schedules (integer artefacts) ----------------------------------------------------------------
+void build_colouring(Grid& g) {
+  // First-fit in ascending row order on the structurally symmetrised graph of the rows the sweep visits;
+  // the regularisation row takes the last colour (contract stated in oracle/mmg_oracle.cpp:build_colouring).
+  HostCsr A;
+  hyb_to_csr(g.Lap, A, g.stream);
+  const int R = A.rows;
+  const int reg = g.Lap.reg_row;
+  auto swept = [&](int i) { return i == reg || g.bcflags[i] == 0; };
+  std::vector<int> tcnt(R + 1, 0);
+  for (int i = 0; i < R; i++) {
+    if (i == reg || !swept(i)) continue;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++) { const int j = A.idx[k]; if (j != reg && j != i && swept(j)) tcnt[j + 1]++; }
+  }
+  for (int i = 0; i < R; i++) tcnt[i + 1] += tcnt[i];
+  std::vector<int> tidx(tcnt[R]), pos(tcnt.begin(), tcnt.end() - 1);
+  for (int i = 0; i < R; i++) {
+    if (i == reg || !swept(i)) continue;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++) { const int j = A.idx[k]; if (j != reg && j != i && swept(j)) tidx[pos[j]++] = i; }
+  }
+  std::vector<int> colour(R, -1), mark;
+  int ncol = 0;
+  for (int i = 0; i < R; i++) {
+    if (i == reg || !swept(i)) continue;
+    auto touch = [&](int j) {
+      if (j < i && j != reg && colour[j] >= 0) {
+        if ((int)mark.size() <= colour[j]) mark.resize(colour[j] + 1, -1);
+        mark[colour[j]] = i;
+      }
+    };
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++) touch(A.idx[k]);
+    for (int k = tcnt[i]; k < tcnt[i + 1]; k++) touch(tidx[k]);
+    int c = 0;
+    while (c < (int)mark.size() && mark[c] == i) c++;
+    colour[i] = c;
+    ncol = std::max(ncol, c + 1);
+  }
+  if (reg >= 0) { colour[reg] = ncol; ncol++; }
+  g.colour_host = colour;
+  g.n_colours = ncol;
+  g.colour_ptr.assign(ncol + 1, 0);
+  for (int i = 0; i < R; i++) if (colour[i] >= 0) g.colour_ptr[colour[i] + 1]++;
+  for (int c = 0; c < ncol; c++) g.colour_ptr[c + 1] += g.colour_ptr[c];
+  std::vector<int> rows(g.colour_ptr[ncol]), cp(g.colour_ptr.begin(), g.colour_ptr.end() - 1);
+  for (int i = 0; i < R; i++) if (colour[i] >= 0) rows[cp[colour[i]]++] = i;
+  g.colour_rows.upload(rows, g.stream);
+  MMG_CUDA(cudaStreamSynchronize(g.stream));
+  g.have_colours = true;
+}
+
+void compute_lex_levels(Grid& g, std::vector<int>& level, int& n_levels) {
+  HostCsr A;
+  hyb_to_csr(g.Lap, A, g.stream);
+  const int R = A.rows, reg = g.Lap.reg_row;
+  level.assign(R, -1);
+  n_levels = 0;
+  for (int i = 0; i < R; i++) {
+    const bool swept = i == reg || g.bcflags[i] == 0;
+    if (!swept) continue;
+    int l = 0;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++) { const int j = A.idx[k]; if (j < i && level[j] >= 0) l = std::max(l, level[j] + 1); }
+    level[i] = l;
+    n_levels = std::max(n_levels, l + 1);
+  }
+}
+
+}  // namespace mmg

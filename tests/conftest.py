@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def libmmg():
+    """The CUDA library, built in-tree.  GPU tests must run on it — never on a fallback."""
+    from meshlessmultigridpoisson_b200 import build, capi
+
+    build.build()
+    return capi.load()

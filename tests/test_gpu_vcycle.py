@@ -1,0 +1,95 @@
+"""V-cycle parity: residual history within 1e-10 relative per cycle (lexicographic, reference-faithful
+mode against the oracle; multicolour mode against the oracle's multicolour restatement) and final
+solution within 1e-8 relative L2."""
+import numpy as np
+import pytest
+
+import oracle
+from meshlessmultigridpoisson_b200 import capi
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL_HISTORY = 1e-10     # per cycle, relative (north star)
+TOL_SOLUTION = 1e-8     # relative L2 (north star)
+FLOOR = 1e-11           # below this the residual is rounding noise of the fp64 solve itself
+
+
+def run_pair(sizes, kind, fine_poly, cycles, multicolour=False, fracstep=False):
+    mg = oracle.make_hierarchy(sizes, kind=kind, fine_poly=fine_poly, fracstep=fracstep)
+    s = H.gpu_solver_from_oracle(mg, fracstep=fracstep)
+    if fracstep:
+        mg.L.orc_fs_step_pre(mg.h, mg.nlevels - 1)
+        s.grid(-1).source_ = mg.level(-1).source
+    mg.set_multicolour(multicolour)
+    s.set_smoother(capi.MULTICOLOUR if multicolour else capi.LEXICOGRAPHIC)
+    mg.vcycle(cycles)
+    s.vCycle(cycles)
+    return mg, s
+
+
+def check_history(mg, s):
+    ho, hg = mg.history(), s.residuals_
+    assert ho.size == hg.size
+    live = np.isfinite(ho) & (ho > FLOOR * ho[0]) & (ho < 1e100)
+    assert live.sum() >= min(5, ho.size)
+    rel = np.abs(hg[live] - ho[live]) / ho[live]
+    assert rel.max() < TOL_HISTORY, rel
+
+
+@pytest.mark.parametrize("fine_poly", [4, 6])
+@pytest.mark.parametrize("multicolour", [False, True])
+def test_dirichlet_config1(libmmg, fine_poly, multicolour):
+    # BASELINE config 1: ~10k nodes, 4 levels (13/25/50/100 lattice sides)
+    mg, s = run_pair([13, 25, 50, 100], oracle.KIND_DIRICHLET, fine_poly, 25, multicolour)
+    check_history(mg, s)
+    assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
+
+
+@pytest.mark.parametrize("multicolour", [False, True])
+def test_mixed_bc(libmmg, multicolour):
+    mg, s = run_pair([13, 25, 50], oracle.KIND_MIXED, 4, 20, multicolour)
+    check_history(mg, s)
+    assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
+
+
+@pytest.mark.parametrize("multicolour", [False, True])
+def test_pure_neumann(libmmg, multicolour):
+    mg, s = run_pair([13, 25, 50], oracle.KIND_NEUMANN, 3, 20, multicolour)
+    check_history(mg, s)
+    assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
+
+
+def test_fracstep_ppe(libmmg):
+    mg, s = run_pair([13, 25, 50], oracle.KIND_PPE, 3, 15, fracstep=True)
+    check_history(mg, s)
+    assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
+
+
+def test_two_level_quirk(libmmg):
+    # 2-level hierarchy: boundaryOp("coarse") of multigrid.cpp:91 zeroes the FINEST grid's Dirichlet values
+    mg, s = run_pair([25, 50], oracle.KIND_DIRICHLET, 4, 10)
+    check_history(mg, s)
+
+
+def test_single_grid_fracstep_shortcut(libmmg):
+    mg, s = run_pair([25], oracle.KIND_PPE, 3, 3, fracstep=True)   # FracStepMultigrid.cpp:64-67
+    assert mg.history().size == 0 and s.residuals_.size == 0
+    assert H.rel_err(s.grid(0).values_, mg.level(0).values) < 1e-11
+
+
+def test_solve_to_tolerance_matches_cycle_count(libmmg):
+    mg = oracle.make_hierarchy([13, 25, 50, 100], kind=oracle.KIND_DIRICHLET, fine_poly=4)
+    s = H.gpu_solver_from_oracle(mg)
+    n_o, _ = mg.solve(1e-8, 200)
+    n_g, r = s.solve(1e-8, 200)
+    assert n_o == n_g and r < 1e-8
+    assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
+
+
+def test_multicolour_and_lexicographic_reach_the_same_solution(libmmg):
+    mg = oracle.make_hierarchy([13, 25, 50], kind=oracle.KIND_DIRICHLET, fine_poly=4)
+    a, b = H.gpu_solver_from_oracle(mg), H.gpu_solver_from_oracle(mg)
+    b.set_smoother(capi.MULTICOLOUR)
+    a.solve(1e-12, 300); b.solve(1e-12, 300)
+    assert H.rel_l2(b.grid(-1).values_, a.grid(-1).values_) < TOL_SOLUTION
