@@ -19,6 +19,7 @@ BC_DIRICHLET, BC_NEUMANN = 1, 2
 FINE, COARSE = 0, 1
 LEXICOGRAPHIC, MULTICOLOUR = 0, 1
 FLAVOUR_MULTIGRID, FLAVOUR_FRACSTEP = 0, 1
+ARITH_REFERENCE_ORDER, ARITH_FAST = 0, 1
 MAT_LAPLACE, MAT_NEUMANN_COEFFS, MAT_RESTRICT, MAT_PROLONG, MAT_DERIVX, MAT_DERIVY, MAT_UVLAPLACE = range(7)
 T_SOR, T_RESIDUAL, T_RESTRICT, T_PROLONG, T_OTHER, T_COUNT = range(6)
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "mmg_grid_push_inhomog_to_rhs": [_vp],
     "mmg_grid_boundary_op": [_vp, _i],
     "mmg_grid_bound_eval_neumann": [_vp],
+    "mmg_grid_set_arithmetic": [_vp, _i],
     "mmg_grid_sor": [_vp, _i],
     "mmg_grid_residual": [_vp, _dp],
     "mmg_grid_fix_vector_bound_coarse": [_vp, _dp],
@@ -92,6 +94,7 @@ SIGNATURES = {
     "mmg_solver_restrict": [_vp, _i],
     "mmg_solver_prolong_correct": [_vp, _i],
     "mmg_solver_coarse_solve": [_vp],
+    "mmg_solver_set_arithmetic": [_vp, _i],
     "mmg_solver_vcycle": [_vp, _i],
     "mmg_solver_residual": [_vp, C.POINTER(_d)],
     "mmg_solver_history_len": [_vp, C.POINTER(_i)],
@@ -302,6 +305,9 @@ class Grid:
     def bound_eval_neumann(self):
         _ck(self.L, self.L.mmg_grid_bound_eval_neumann(self.h))
 
+    def set_arithmetic(self, arithmetic):
+        _ck(self.L, self.L.mmg_grid_set_arithmetic(self.h, arithmetic))
+
     def sor(self, smoother=LEXICOGRAPHIC):
         _ck(self.L, self.L.mmg_grid_sor(self.h, smoother))
 
@@ -409,6 +415,9 @@ class Multigrid:
 
     def set_smoother(self, smoother):
         _ck(self.L, self.L.mmg_solver_set_smoother(self.h, smoother))
+
+    def set_arithmetic(self, arithmetic):
+        _ck(self.L, self.L.mmg_solver_set_arithmetic(self.h, arithmetic))
 
     def restrict(self, level):
         _ck(self.L, self.L.mmg_solver_restrict(self.h, level))

@@ -324,6 +324,13 @@ int mmg_grid_bound_eval_neumann(mmg_grid* g) {
   op_bound_eval_neumann(G(g));
   API_END
 }
+int mmg_grid_set_arithmetic(mmg_grid* g, int arithmetic) {
+  API_BEGIN
+  NEED(g);
+  MMG_REQUIRE(arithmetic == MMG_ARITH_REFERENCE_ORDER || arithmetic == MMG_ARITH_FAST, MMG_ERR_ARG, "unknown arithmetic mode");
+  G(g).exact = arithmetic == MMG_ARITH_REFERENCE_ORDER;
+  API_END
+}
 int mmg_grid_sor(mmg_grid* g, int smoother) {
   API_BEGIN
   NEED(g);
@@ -545,6 +552,7 @@ int mmg_solver_add_grid(mmg_solver* s, mmg_grid* g) {
   gr->sync();
   if (gr->own_stream) { cudaStreamDestroy(gr->stream); gr->own_stream = false; }
   gr->stream = so.stream;               // one stream for the whole cycle
+  gr->exact = so.arithmetic == MMG_ARITH_REFERENCE_ORDER;
   gr->timers = &so.timers;
   so.grids.push_back(gr);
   std::sort(so.grids.begin(), so.grids.end(), [](Grid* a, Grid* b) { return a->n != b->n ? a->n < b->n : a < b; });  // multigrid.cpp:116-122
@@ -686,6 +694,14 @@ int mmg_solver_coarse_solve(mmg_solver* s) {
   op_sor(c, so.smoother);
   MMG_CUDA(cudaStreamSynchronize(so.stream));
   solver_check_abort(so);
+  API_END
+}
+int mmg_solver_set_arithmetic(mmg_solver* s, int arithmetic) {
+  API_BEGIN
+  NEED(s);
+  MMG_REQUIRE(arithmetic == MMG_ARITH_REFERENCE_ORDER || arithmetic == MMG_ARITH_FAST, MMG_ERR_ARG, "unknown arithmetic mode");
+  S(s).arithmetic = arithmetic;
+  for (Grid* g : S(s).grids) g->exact = arithmetic == MMG_ARITH_REFERENCE_ORDER;
   API_END
 }
 int mmg_solver_vcycle(mmg_solver* s, int n_cycles) {

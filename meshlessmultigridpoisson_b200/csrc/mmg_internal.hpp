@@ -141,6 +141,7 @@ struct Grid {
   int n = 0;        // laplaceMatSize_
   int A = 0;        // rows of laplaceMat_ (n, or n+1 with any Neumann boundary)
   bool neumann = false, implicit = false;
+  bool exact = true;   // reference-order arithmetic (bit-faithful parity mode) vs reordered warp reductions (throughput mode)
   mmg_props props{};
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -181,6 +182,7 @@ struct Grid {
 struct Solver {
   int flavour = MMG_FLAVOUR_MULTIGRID;
   int smoother = MMG_SMOOTHER_LEXICOGRAPHIC;
+  int arithmetic = MMG_ARITH_REFERENCE_ORDER;
   std::vector<Grid*> grids;                 // sorted ascending by (size, pointer), like multigrid.cpp:116-122
   std::vector<HybMatrix*> restrict_, prolong_;  // [i] as in the reference (restrict_[0]==nullptr, prolong_.back()==nullptr)
   DevBuf<double> hist;                      // residuals_ on device

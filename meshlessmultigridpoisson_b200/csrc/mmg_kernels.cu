@@ -365,6 +365,242 @@ __global__ void __launch_bounds__(kBlock) k_bound_eval(HybView A, const int* __r
   }
 }
 
+// ================================================================================================
+// Reference-order ("exact") variants.  The reference accumulates every row sum sequentially in
+// ascending column order (Eigen's row loop, Grid::sor, Grid::bound_eval_neumann).  A V-cycle
+// residual history can only be reproduced to 1e-10 *relative per cycle* all the way down to the
+// convergence floor if the sums are rounded identically, so the parity mode keeps that order:
+// lanes fetch a row's entries coalesced and form the products in parallel, then the warp folds
+// the products one by one in column order (a shuffle broadcast feeding a serial DADD chain).
+// Results are bit-identical to the oracle for Dirichlet grids.
+// ================================================================================================
+
+// s <- s (+/-) p_k for the 32 products held one per lane, in lane order, first `cnt` lanes only.
+// `dcol` handling: when a diagonal product is pending (diag-first storage) it is inserted just
+// before the first entry whose column exceeds `row`, i.e. at its ascending-column position.
+__device__ __forceinline__ double fold_in_order(double s, double p, int col, int cnt, bool subtract, bool& diag_pending, double pdiag, int row) {
+#pragma unroll
+  for (int l = 0; l < 32; l++) {
+    if (l < cnt) {
+      const double pl = __shfl_sync(0xffffffffu, p, l);
+      const int cl = __shfl_sync(0xffffffffu, col, l);
+      if (diag_pending && cl > row) { s = subtract ? __dsub_rn(s, pdiag) : __dadd_rn(s, pdiag); diag_pending = false; }
+      s = subtract ? __dsub_rn(s, pl) : __dadd_rn(s, pl);
+    }
+  }
+  return s;
+}
+
+// in-order row dot product; all lanes return the same value.  skip_diag: SOR-style sums leave the diagonal out.
+__device__ __forceinline__ double row_dot_in_order(const HybView& A, int row, const double* x, bool diag_first, bool skip_diag, bool subtract, double s0,
+                                                   double* diag_out) {
+  const int lane = threadIdx.x & 31;
+  const int len = A.len[row];
+  const double* __restrict__ v = row_val(A, row);
+  const int* __restrict__ c = row_col(A, row);
+  const int m = len < A.W ? len : A.W;
+  double s = s0, pdiag = 0.0;
+  bool diag_pending = false;
+  int first = 0;
+  if (diag_first && m > 0) {
+    const double d = v[0];
+    if (diag_out) *diag_out = d;
+    if (!skip_diag) { pdiag = __dmul_rn(d, x[c[0]]); diag_pending = true; }
+    first = 1;
+  }
+  for (int base = first; base < m; base += 32) {
+    const int k = base + lane;
+    double p = 0.0;
+    int col = 0x7fffffff;
+    if (k < m) { col = c[k]; p = __dmul_rn(v[k], x[col]); }
+    s = fold_in_order(s, p, col, min(32, m - base), subtract, diag_pending, pdiag, row);
+  }
+  if (len > A.W) {
+    const int o = ovf_find(A, row);
+    const int e = A.ovf_ptr[o + 1];
+    for (int base = A.ovf_ptr[o]; base < e; base += 32) {
+      const int k = base + lane;
+      double p = 0.0;
+      int col = 0x7fffffff;
+      if (k < e) { col = A.ovf_col[k]; p = __dmul_rn(A.ovf_val[k], x[col]); }
+      s = fold_in_order(s, p, col, min(32, e - base), subtract, diag_pending, pdiag, row);
+    }
+  }
+  if (diag_pending) s = subtract ? __dsub_rn(s, pdiag) : __dadd_rn(s, pdiag);
+  return s;
+}
+
+__global__ void __launch_bounds__(kBlock) k_spmv_exact(HybView A, int diag_first, const double* x, const double* __restrict__ b, double* y,
+                                                       const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
+                                                       double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double num = 0.0, den = 0.0;
+  for (int row = warp; row < A.rows; row += nwarps) {
+    const double acc = row_dot_in_order(A, row, x, diag_first != 0, false, false, 0.0, nullptr);
+    if (lane == 0) {
+      const int flag = rowflag ? rowflag[row] : 0;
+      if (op == OP_SPMV) {
+        y[row] = acc;
+      } else if (op == OP_RESID) {
+        const double bi = b[row];
+        double t = __dsub_rn(bi, acc);
+        if (flag == 1) t = 0.0;
+        if (y) y[row] = t;
+        num += fabs(t);
+        den += fabs(bi);
+      } else if (op == OP_PROLONG) {
+        if (!(mask_dirichlet && flag == 1)) y[row] = __dadd_rn(y[row], acc);
+      } else {
+        double t = acc;
+        if (flag == 1) t = 0.0;
+        if (mask_neumann && flag == 2) t = 0.0;
+        y[row] = t;
+      }
+    }
+  }
+  if (partial) {
+    block_sum2(num, den);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = num; partial[2 * blockIdx.x + 1] = den; }
+  }
+}
+
+// regularisation row, sequential: partial[0] = sum_j val[j]*x[col[j]] in ascending column order (one warp)
+__global__ void __launch_bounds__(32) k_regdot_exact(const int* __restrict__ col, const double* __restrict__ val, int len, const double* x, double* partial) {
+  const int lane = threadIdx.x;
+  double s = 0.0;
+  for (int base = 0; base < len; base += 32) {
+    const int j = base + lane;
+    const double p = j < len ? __dmul_rn(val[j], x[col[j]]) : 0.0;
+    const int cnt = min(32, len - base);
+#pragma unroll
+    for (int l = 0; l < 32; l++)
+      if (l < cnt) s = __dadd_rn(s, __shfl_sync(0xffffffffu, p, l));
+  }
+  if (lane == 0) partial[0] = s;
+}
+
+// Lexicographic sweep, reference-order arithmetic: warp per row; products wait on their dependencies
+// in parallel, then the row sum is folded in ascending column order.
+template <int T>
+__global__ void __launch_bounds__(kBlock) k_sor_lex_exact(HybView A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b,
+                                                          const double* __restrict__ x_old, double* x_new, double omega, int* abort_flag,
+                                                          long long timeout_cycles) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long t_start = clock64();
+  for (int row = warp; row < A.rows; row += nwarps) {
+    if (rowflag[row] != 0) continue;
+    const int len = A.len[row];
+    const double* __restrict__ v = row_val(A, row);
+    const int* __restrict__ c = row_col(A, row);
+    const int m = len < A.W ? len : A.W;
+    double prod[T];
+    double pv[T];
+    int pc[T];
+    unsigned pend = 0;
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      const int k = 1 + lane + t * 32;     // slot 0 is the diagonal
+      prod[t] = 0.0; pv[t] = 0.0; pc[t] = 0;
+      if (k < m) {
+        const double a = v[k];
+        const int col = c[k];
+        if (col > row) prod[t] = __dmul_rn(a, __ldg(x_old + col));
+        else { pv[t] = a; pc[t] = col; pend |= 1u << t; }
+      }
+    }
+    const double diag = v[0];
+    unsigned spins = 0;
+    bool aborted = false;
+    while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        if (pend & (1u << t)) {
+          const double xv = ld_relaxed(x_new + pc[t]);
+          if (!is_sentinel(xv)) { prod[t] = __dmul_rn(pv[t], xv); pend &= ~(1u << t); }
+        }
+      }
+      if ((++spins & 0xff) == 0) {
+        if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
+      }
+    }
+    if (aborted) { if (lane == 0) st_relaxed(x_new + row, 0.0); return; }
+    double s = 0.0;                          // x_i = 0; x_i -= a_ij * v_j, ascending j (grid.cpp:122-136)
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      const int cnt = min(32, m - 1 - t * 32);
+#pragma unroll
+      for (int l = 0; l < 32; l++)
+        if (l < cnt) s = __dsub_rn(s, __shfl_sync(0xffffffffu, prod[t], l));
+    }
+    if (len > A.W) {  // spill rows: blocking in-order tail
+      const int o = ovf_find(A, row);
+      const int e = A.ovf_ptr[o + 1];
+      for (int base = A.ovf_ptr[o]; base < e; base += 32) {
+        const int k = base + lane;
+        double p = 0.0;
+        if (k < e) {
+          const int col = A.ovf_col[k];
+          double xv;
+          if (col > row) xv = __ldg(x_old + col);
+          else {
+            xv = ld_relaxed(x_new + col);
+            while (is_sentinel(xv)) {
+              if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); xv = 0.0; break; }
+              xv = ld_relaxed(x_new + col);
+            }
+          }
+          p = __dmul_rn(A.ovf_val[k], xv);
+        }
+        const int cnt = min(32, e - base);
+#pragma unroll
+        for (int l = 0; l < 32; l++)
+          if (l < cnt) s = __dsub_rn(s, __shfl_sync(0xffffffffu, p, l));
+      }
+    }
+    if (lane == 0) {                         // x+=b; x*=w/d; x+=(1-w)x_old (grid.cpp:137-141)
+      double xi = __dadd_rn(s, b[row]);
+      xi = __dmul_rn(xi, omega / diag);
+      xi = __dadd_rn(xi, __dmul_rn(1 - omega, x_old[row]));
+      st_relaxed(x_new + row, xi);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_sor_mc_exact(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
+                                                         double omega) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < count; i += nwarps) {
+    const int row = rows_list[i];
+    double diag = 0.0;
+    const double s = row_dot_in_order(A, row, x, true, true, true, 0.0, &diag);
+    if (lane == 0) {
+      double xi = __dadd_rn(s, b[row]);
+      xi = __dmul_rn(xi, omega / diag);
+      xi = __dadd_rn(xi, __dmul_rn(1 - omega, x[row]));
+      x[row] = xi;
+    }
+  }
+}
+
+// t = b_c; t -= v_k * a_ck ascending k != c; t /= a_cc  (grid.cpp:84-98)
+__global__ void __launch_bounds__(kBlock) k_bound_eval_exact(HybView A, const int* __restrict__ nodes, int count, const double* __restrict__ b, double* x) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < count; i += nwarps) {
+    const int row = nodes[i];
+    double diag = 0.0;
+    const double t = row_dot_in_order(A, row, x, true, true, true, b[row], &diag);
+    if (lane == 0) x[row] = t / diag;
+  }
+}
+
 __global__ void k_scatter(const int* __restrict__ idx, const double* __restrict__ vals, int count, double* dst, int use_zero) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) dst[idx[i]] = use_zero ? 0.0 : vals[i];
@@ -406,8 +642,15 @@ void dispatch_lpr(int W, F&& f) {
 }
 
 void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
-                 double* partial, int* nblocks_out, int device, cudaStream_t s) {
+                 double* partial, int* nblocks_out, int device, cudaStream_t s, bool exact) {
   const int sms = sm_count_of(device);
+  if (exact) {
+    const int blocks = grid_for(M.rows, 32, sms);
+    if (nblocks_out) *nblocks_out = blocks;
+    k_spmv_exact<<<blocks, kBlock, 0, s>>>(M.view(), M.diag_first ? 1 : 0, x, b, y, rowflag, op, mask_d, mask_n, partial);
+    MMG_CUDA(cudaGetLastError());
+    return;
+  }
   dispatch_lpr(M.W, [&](auto L) {
     constexpr int LPR = decltype(L)::value;
     const int blocks = grid_for(M.rows, LPR, sms);
@@ -570,6 +813,20 @@ void hyb_to_csr(const HybMatrix& M, HostCsr& A, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // operations
 // ------------------------------------------------------------------------------------------------
+// off-diagonal dot product of the regularisation row; returns how many partials were written
+static int launch_regdot(Grid& g, const double* x, double* reg_partial) {
+  const HybMatrix& L = g.Lap;
+  if (L.reg_row < 0) return 0;
+  if (g.exact) {
+    k_regdot_exact<<<1, 32, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, x, reg_partial);
+    MMG_CUDA(cudaGetLastError());
+    return 1;
+  }
+  k_regdot<<<kRegBlocks, kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, x, reg_partial);
+  MMG_CUDA(cudaGetLastError());
+  return kRegBlocks;
+}
+
 static void residual_impl(Grid& g, double* r_out, double* ratio_dev) {
   const HybMatrix& L = g.Lap;
   MMG_REQUIRE(g.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
@@ -581,12 +838,9 @@ static void residual_impl(Grid& g, double* r_out, double* ratio_dev) {
   int nb = 0;
   {
     TimedScope ts(g.timers, MMG_T_RESIDUAL, g.stream, L.matrix_bytes() + (int64_t)g.A * 24, 2 + (L.reg_row >= 0));
-    launch_spmv(L, g.x.p, g.b.p, r_out, g.rowflag.p, OP_RESID, 0, 0, norm_partial, &nb, g.device, g.stream);
-    if (L.reg_row >= 0) {
-      k_regdot<<<kRegBlocks, kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, g.x.p, reg_partial);
-      MMG_CUDA(cudaGetLastError());
-    }
-    k_finish_residual<<<1, kBlock, 0, g.stream>>>(norm_partial, nb, reg_partial, kRegBlocks, L.reg_row, L.reg_diag, g.x.p, g.b.p, r_out, ratio_dev);
+    launch_spmv(L, g.x.p, g.b.p, r_out, g.rowflag.p, OP_RESID, 0, 0, norm_partial, &nb, g.device, g.stream, g.exact);
+    const int n_reg = launch_regdot(g, g.x.p, reg_partial);
+    k_finish_residual<<<1, kBlock, 0, g.stream>>>(norm_partial, nb, reg_partial, n_reg, L.reg_row, L.reg_diag, g.x.p, g.b.p, r_out, ratio_dev);
     MMG_CUDA(cudaGetLastError());
   }
 }
@@ -599,10 +853,14 @@ void op_bound_eval_neumann(Grid& g) {
   MMG_REQUIRE(g.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
   const int sms = sm_count_of(g.device);
   TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.neu_pts.n * (12 * g.Lap.W + 24));
-  dispatch_lpr(g.Lap.W, [&](auto Lc) {
-    constexpr int LPR = decltype(Lc)::value;
-    k_bound_eval<LPR><<<grid_for((int)g.neu_pts.n, LPR, sms), kBlock, 0, g.stream>>>(g.Lap.view(), g.neu_pts.p, (int)g.neu_pts.n, g.b.p, g.x.p);
-  });
+  if (g.exact) {
+    k_bound_eval_exact<<<grid_for((int)g.neu_pts.n, 32, sms), kBlock, 0, g.stream>>>(g.Lap.view(), g.neu_pts.p, (int)g.neu_pts.n, g.b.p, g.x.p);
+  } else {
+    dispatch_lpr(g.Lap.W, [&](auto Lc) {
+      constexpr int LPR = decltype(Lc)::value;
+      k_bound_eval<LPR><<<grid_for((int)g.neu_pts.n, LPR, sms), kBlock, 0, g.stream>>>(g.Lap.view(), g.neu_pts.p, (int)g.neu_pts.n, g.b.p, g.x.p);
+    });
+  }
   MMG_CUDA(cudaGetLastError());
 }
 
@@ -634,7 +892,7 @@ void op_zero_values(Grid& g) {
 
 void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class) {
   TimedScope ts(ctx.timers, timer_class, ctx.stream, M.matrix_bytes() + (int64_t)M.rows * 8 + (int64_t)M.cols * 8);
-  launch_spmv(M, x_dev, nullptr, y_dev, nullptr, OP_SPMV, 0, 0, nullptr, nullptr, ctx.device, ctx.stream);
+  launch_spmv(M, x_dev, nullptr, y_dev, nullptr, OP_SPMV, 0, 0, nullptr, nullptr, ctx.device, ctx.stream, ctx.exact);
 }
 
 void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fine_res_dev) {
@@ -643,7 +901,7 @@ void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fin
     TimedScope ts(fine.timers, MMG_T_RESTRICT, fine.stream, R.matrix_bytes() + (int64_t)coarse.n * 8 + (int64_t)fine.n * 8);
     // fix_vector_bound_coarse on the coarse source and, if the FINE grid is Neumann, modify_coeff_neumann("coarse"):
     // both are masks on the output rows (multigrid.cpp:82-86)
-    launch_spmv(R, fine_res_dev, nullptr, coarse.b.p, coarse.rowflag.p, OP_RESTRICT, 1, fine.neumann ? 1 : 0, nullptr, nullptr, fine.device, fine.stream);
+    launch_spmv(R, fine_res_dev, nullptr, coarse.b.p, coarse.rowflag.p, OP_RESTRICT, 1, fine.neumann ? 1 : 0, nullptr, nullptr, fine.device, fine.stream, fine.exact);
   }
   if (fine.neumann) {  // source_(rows-1)=0 (multigrid.cpp:84) and the same store inside modify_coeff_neumann (grid.cpp:71)
     TimedScope ts(fine.timers, MMG_T_OTHER, fine.stream, 8);
@@ -655,14 +913,14 @@ void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fin
 void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P) {
   MMG_REQUIRE(P.rows == fine.n && P.cols == coarse.n, MMG_ERR_STATE, "prolongation matrix shape does not match the grids");
   TimedScope ts(fine.timers, MMG_T_PROLONG, fine.stream, P.matrix_bytes() + (int64_t)fine.n * 16 + (int64_t)coarse.n * 8);
-  launch_spmv(P, coarse.x.p, nullptr, fine.x.p, fine.rowflag.p, OP_PROLONG, fine.neumann ? 0 : 1, 0, nullptr, nullptr, fine.device, fine.stream);
+  launch_spmv(P, coarse.x.p, nullptr, fine.x.p, fine.rowflag.p, OP_PROLONG, fine.neumann ? 0 : 1, 0, nullptr, nullptr, fine.device, fine.stream, fine.exact);
 }
 
 // ---- SOR -----------------------------------------------------------------------------------------
-template <int LPR, int T>
-static void launch_lex(Grid& g, const double* x_old, double* x_new) {
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_lex<LPR, T>, kBlock, 0));
+template <class K>
+static void launch_lex_kernel(Grid& g, K kernel, int LPR, const double* x_old, double* x_new) {
+  int blocks_per_sm = 0;
+  MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kBlock, 0));
   const int sms = sm_count_of(g.device);
   int blocks = blocks_per_sm * sms;
   static int cap = -1;
@@ -677,8 +935,12 @@ static void launch_lex(Grid& g, const double* x_old, double* x_new) {
   int* abortp = g.abort_flag.p;
   long long timeout = 6000000000ll;  // ~3 s of SM clocks
   void* args[] = {&A, &rf, &b, &x_old, &x_new, &omega, &abortp, &timeout};
-  MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_lex<LPR, T>, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+  MMG_CUDA(cudaLaunchCooperativeKernel((void*)kernel, dim3(blocks), dim3(kBlock), args, 0, g.stream));
 }
+template <int LPR, int T>
+static void launch_lex(Grid& g, const double* x_old, double* x_new) { launch_lex_kernel(g, k_sor_lex<LPR, T>, LPR, x_old, x_new); }
+template <int T>
+static void launch_lex_exact(Grid& g, const double* x_old, double* x_new) { launch_lex_kernel(g, k_sor_lex_exact<T>, 32, x_old, x_new); }
 
 static void sor_lex_sweep(Grid& g) {
   const HybMatrix& L = g.Lap;
@@ -689,7 +951,11 @@ static void sor_lex_sweep(Grid& g) {
   double* x_new = g.x_alt.p;
   k_sweep_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, x_old, x_new, L.rows, g.A);
   MMG_CUDA(cudaGetLastError());
-#define LEX_CASE(LPR_, T_) if (lpr == LPR_ && T <= T_) { launch_lex<LPR_, T_>(g, x_old, x_new); } else
+  const int Te = (W - 1 + 31) / 32;
+#define LEXE_CASE(T_) if (g.exact && Te <= T_) { launch_lex_exact<T_>(g, x_old, x_new); } else
+  LEXE_CASE(1) LEXE_CASE(2) LEXE_CASE(3) LEXE_CASE(4) LEXE_CASE(6) LEXE_CASE(8)
+#undef LEXE_CASE
+#define LEX_CASE(LPR_, T_) if (!g.exact && lpr == LPR_ && T <= T_) { launch_lex<LPR_, T_>(g, x_old, x_new); } else
   LEX_CASE(32, 1) LEX_CASE(32, 2) LEX_CASE(32, 3) LEX_CASE(32, 4) LEX_CASE(32, 6) LEX_CASE(32, 8)
   LEX_CASE(16, 2) LEX_CASE(16, 3)
   LEX_CASE(8, 1) LEX_CASE(8, 2) LEX_CASE(8, 3)
@@ -697,8 +963,8 @@ static void sor_lex_sweep(Grid& g) {
 #undef LEX_CASE
   if (L.reg_row >= 0) {
     double* reg_partial = g.partials.p;
-    k_regdot<<<kRegBlocks, kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, x_new, reg_partial);
-    k_finish_sor_reg<<<1, kBlock, 0, g.stream>>>(reg_partial, kRegBlocks, L.reg_row, L.reg_diag, g.props.omega, g.b.p, x_old, x_new);
+    const int n_reg = launch_regdot(g, x_new, reg_partial);
+    k_finish_sor_reg<<<1, kBlock, 0, g.stream>>>(reg_partial, n_reg, L.reg_row, L.reg_diag, g.props.omega, g.b.p, x_old, x_new);
     MMG_CUDA(cudaGetLastError());
   }
   std::swap(g.x.p, g.x_alt.p);
@@ -708,19 +974,27 @@ static void sor_mc_sweep(Grid& g) {
   const HybMatrix& L = g.Lap;
   const int sms = sm_count_of(g.device);
   const int ncol_rows = L.reg_row >= 0 ? g.n_colours - 1 : g.n_colours;  // the regularisation row is the last colour
-  dispatch_lpr(L.W, [&](auto Lc) {
-    constexpr int LPR = decltype(Lc)::value;
+  if (g.exact) {
     for (int c = 0; c < ncol_rows; c++) {
       const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
       if (count == 0) continue;
-      k_sor_mc<LPR><<<grid_for(count, LPR, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
+      k_sor_mc_exact<<<grid_for(count, 32, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
     }
-  });
+  } else {
+    dispatch_lpr(L.W, [&](auto Lc) {
+      constexpr int LPR = decltype(Lc)::value;
+      for (int c = 0; c < ncol_rows; c++) {
+        const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
+        if (count == 0) continue;
+        k_sor_mc<LPR><<<grid_for(count, LPR, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
+      }
+    });
+  }
   MMG_CUDA(cudaGetLastError());
   if (L.reg_row >= 0) {
     double* reg_partial = g.partials.p;
-    k_regdot<<<kRegBlocks, kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, g.x.p, reg_partial);
-    k_finish_sor_reg<<<1, kBlock, 0, g.stream>>>(reg_partial, kRegBlocks, L.reg_row, L.reg_diag, g.props.omega, g.b.p, g.x.p, g.x.p);
+    const int n_reg = launch_regdot(g, g.x.p, reg_partial);
+    k_finish_sor_reg<<<1, kBlock, 0, g.stream>>>(reg_partial, n_reg, L.reg_row, L.reg_diag, g.props.omega, g.b.p, g.x.p, g.x.p);
     MMG_CUDA(cudaGetLastError());
   }
 }

@@ -22,12 +22,25 @@ CASES = {
 }
 
 
-@pytest.fixture(scope="module", params=sorted(CASES))
+ARITH = {"reference_order": capi.ARITH_REFERENCE_ORDER, "fast": capi.ARITH_FAST}
+
+
+@pytest.fixture(scope="module", params=[(c, a) for c in sorted(CASES) for a in sorted(ARITH)], ids=lambda p: "%s-%s" % p)
 def pair(request, libmmg):
-    cfg = CASES[request.param]
+    cfg = CASES[request.param[0]]
     mg = oracle.make_hierarchy(cfg["sizes"], kind=cfg["kind"], fine_poly=cfg["fine_poly"])
     s = H.gpu_solver_from_oracle(mg)
+    s.set_arithmetic(ARITH[request.param[1]])
+    s.exact = request.param[1] == "reference_order"
     return mg, s
+
+
+def close(s, got, want, tol):
+    """reference-order arithmetic must reproduce the oracle bit for bit; the fast mode to `tol` relative"""
+    if s.exact:
+        assert np.array_equal(got, want), "reference-order mode is not bit-identical (max rel %g)" % H.rel_err(got, want)
+    else:
+        assert H.rel_err(got, want) < tol
 
 
 def test_native_library_is_the_one_loaded(libmmg):
@@ -53,7 +66,7 @@ def test_residual(pair):
         v = H.random_values(lv, 7 + l)
         lv.set_vec(oracle.VEC_VALUES, v)
         g.values_ = v
-        assert H.rel_err(g.residual(), lv.residual()) < TOL_OP
+        close(s, g.residual(), lv.residual(), TOL_OP)
 
 
 def test_residual_norm(pair):
@@ -92,7 +105,7 @@ def test_bound_eval_neumann(pair):
         v = H.random_values(lv, 5 + l)
         lv.set_vec(oracle.VEC_VALUES, v); g.values_ = v
         lv.bound_eval_neumann(); g.bound_eval_neumann()
-        assert H.rel_err(g.values_, lv.values) < TOL_OP
+        close(s, g.values_, lv.values, TOL_OP)
 
 
 def test_push_inhomog_to_rhs(pair):
@@ -120,7 +133,7 @@ def test_sor(pair, smoother):
             lv.sor(); g.sor(capi.LEXICOGRAPHIC)
         else:
             lv.sor_multicolour(); g.sor(capi.MULTICOLOUR)
-        assert H.rel_err(g.values_, lv.values) < 1e-11, (l, smoother)
+        close(s, g.values_, lv.values, 1e-11)
 
 
 def test_schedules_bit_exact(pair):
@@ -152,7 +165,7 @@ def test_restrict_and_prolong(pair):
             coarse.modify_coeff_neumann(True)
             src = coarse.source
         s.restrict(l)
-        assert H.rel_err(s.grid(l - 1).source_, src) < TOL_OP
+        close(s, s.grid(l - 1).source_, src, TOL_OP)
         # prolongation + correction, multigrid.cpp:102-106
         vc = H.random_values(coarse, 41 + l)
         coarse.set_vec(oracle.VEC_VALUES, vc); s.grid(l - 1).values_ = vc
@@ -162,4 +175,4 @@ def test_restrict_and_prolong(pair):
             full = fine.fix_vector_bound_coarse(full)
         expect = v + full
         s.prolong_correct(l)
-        assert H.rel_err(s.grid(l).values_, expect) < TOL_OP
+        close(s, s.grid(l).values_, expect, TOL_OP)

@@ -15,9 +15,10 @@ TOL_SOLUTION = 1e-8     # relative L2 (north star)
 FLOOR = 1e-11           # below this the residual is rounding noise of the fp64 solve itself
 
 
-def run_pair(sizes, kind, fine_poly, cycles, multicolour=False, fracstep=False):
+def run_pair(sizes, kind, fine_poly, cycles, multicolour=False, fracstep=False, fast=False):
     mg = oracle.make_hierarchy(sizes, kind=kind, fine_poly=fine_poly, fracstep=fracstep)
     s = H.gpu_solver_from_oracle(mg, fracstep=fracstep)
+    s.set_arithmetic(capi.ARITH_FAST if fast else capi.ARITH_REFERENCE_ORDER)
     if fracstep:
         mg.L.orc_fs_step_pre(mg.h, mg.nlevels - 1)
         s.grid(-1).source_ = mg.level(-1).source
@@ -29,12 +30,21 @@ def run_pair(sizes, kind, fine_poly, cycles, multicolour=False, fracstep=False):
 
 
 def check_history(mg, s):
+    """reference-order arithmetic: every cycle within 1e-10 RELATIVE of the oracle, down to the floor"""
     ho, hg = mg.history(), s.residuals_
     assert ho.size == hg.size
     live = np.isfinite(ho) & (ho > FLOOR * ho[0]) & (ho < 1e100)
     assert live.sum() >= min(5, ho.size)
     rel = np.abs(hg[live] - ho[live]) / ho[live]
     assert rel.max() < TOL_HISTORY, rel
+
+
+def check_history_fast(mg, s):
+    """throughput arithmetic (reordered sums): the history agrees to 1e-10 of the INITIAL residual; the relative
+    deviation necessarily grows like eps*cond/residual as the residual approaches its rounding floor"""
+    ho, hg = mg.history(), s.residuals_
+    assert ho.size == hg.size
+    assert np.abs(hg - ho).max() < TOL_HISTORY * ho[0]
 
 
 @pytest.mark.parametrize("fine_poly", [4, 6])
@@ -93,3 +103,10 @@ def test_multicolour_and_lexicographic_reach_the_same_solution(libmmg):
     b.set_smoother(capi.MULTICOLOUR)
     a.solve(1e-12, 300); b.solve(1e-12, 300)
     assert H.rel_l2(b.grid(-1).values_, a.grid(-1).values_) < TOL_SOLUTION
+
+
+@pytest.mark.parametrize("multicolour", [False, True])
+def test_fast_arithmetic_history(libmmg, multicolour):
+    mg, s = run_pair([13, 25, 50, 100], oracle.KIND_DIRICHLET, 4, 25, multicolour, fast=True)
+    check_history_fast(mg, s)
+    assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
