@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline benchmark of the multigrid solve path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one V-cycle (Multigrid::vCycle, multigrid.cpp:62-110) on the synthetic workload the metric is
+quoted on: a 4M-node jittered point cloud on the unit square (2000 x 2000 lattice side), manufactured-solution
+Dirichlet Poisson problem, PHS r^3 + polyDeg-4 RBF-FD on the finest level, polyDeg 3 on the coarse levels,
+nu=5 SOR sweeps, omega=1.4 (gen_mg_param, testing_functions.cpp:372-380).  The hierarchy is coarsened 4x per
+level down to a ~16x16 cloud (the reference's own coarsest cloud has 170 nodes), because the reference's
+"coarse solve" is only 2*nu SOR sweeps (multigrid.cpp:92-95).
+
+Reported on ONE JSON line:
+  value / ms_per_step  V-cycles per second, throughput mode (multicolour SOR, reordered row sums), operators resident in HBM
+  e2e                  same metric through the C-ABI with HOST buffers: every step uploads source_ and values_ from pinned
+                       host memory, runs one V-cycle and downloads values_ and the residual
+  lexicographic        the reference-faithful mode (dependency-DAG lexicographic SOR, reference-order row sums), reported separately
+  solve                cycles and seconds to reduce |b-Ax|_1/|b|_1 below 1e-8 (loop shape of FractionalStepSim.cpp:139-142)
+  roofline             the dominant kernel (finest-level SOR sweep): algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline         the CPU oracle (restated reference) on a bounded sample of the same workload, single thread like the reference
+
+`--impl reference` times only the CPU oracle (all host threads for set-up, one thread for the V-cycle — the reference is
+strictly serial) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOL = 1e-8
+
+
+def level_sides(side, levels=None):
+    out = [side]
+    while (levels is None and out[-1] > 16) or (levels is not None and len(out) < levels):
+        out.append((out[-1] + 1) // 2)
+    return out[::-1]
+
+
+def algorithmic_bytes_per_cycle(sides, fine_poly, coarse_poly=3, nu=5):
+    """sum_l>=1 [(2nu+1) B_A(l) + B_R(l) + B_P(l)] + B_A(finest) + 2nu B_A(0), fp64 values + int32 columns."""
+    from meshlessmultigridpoisson_b200.problems import stencil_size
+
+    n_i = stencil_size(fine_poly)          # Multigrid uses the finest grid's polyDeg for every P and R (multigrid.cpp:22,25)
+    L = len(sides)
+    total = 0
+    for l, s in enumerate(sides):
+        N = s * s
+        k = stencil_size(fine_poly if l == L - 1 else coarse_poly)
+        b_a = N * (12 * k + 24)
+        if l >= 1:
+            nc = sides[l - 1] ** 2
+            total += (2 * nu + 1) * b_a + (nc * (12 * n_i + 8) + 8 * N) + (N * (12 * n_i + 16) + 8 * nc)
+        else:
+            total += 2 * nu * b_a
+        if l == L - 1:
+            total += b_a
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l.split(", ") for (_, l) in self.lines[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_cpu_oracle(side, levels_below, fine_poly, cycles, threads_setup):
+    """Bounded sample on the host: same generator/seeds, smaller finest lattice; V-cycle loop single threaded like the
+    reference (std::clock pair, testing_functions.cpp:340-344)."""
+    import oracle
+
+    os.environ["OMP_NUM_THREADS"] = str(threads_setup)
+    sides = level_sides(side)
+    t0 = time.time()
+    mg = oracle.make_hierarchy(sides, kind=oracle.KIND_DIRICHLET, fine_poly=fine_poly)
+    setup_s = time.time() - t0
+    mg.vcycle(1)                                  # warm caches / page in
+    secs = mg.time_vcycles(cycles)
+    return dict(sides=sides, setup_s=setup_s, s_per_cycle=secs / cycles, history=mg.history().tolist())
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    full_sides = level_sides(args.side, args.levels)
+    r = run_cpu_oracle(args.cpu_side, None, args.fine_poly, max(1, args.steps), cores)
+    scale = algorithmic_bytes_per_cycle(r["sides"], args.fine_poly) / algorithmic_bytes_per_cycle(full_sides, args.fine_poly)
+    s_full = r["s_per_cycle"] / scale            # V-cycle cost is linear in the bytes it streams
+    v = 1.0 / s_full
+    sample = ("CPU oracle (restated reference, g++ -O2 -ffp-contract=off), lexicographic SOR, %d V-cycles on a %dx%d-side hierarchy %s "
+              "(%.3f s/cycle), scaled by algorithmic bytes x%.4g to the %dx%d workload; V-cycle loop on 1 thread because the reference is serial"
+              % (max(1, args.steps), args.cpu_side, args.cpu_side, r["sides"], r["s_per_cycle"], 1 / scale, args.side, args.side))
+    line = {
+        "impl": "reference", "metric": "vcycles_per_s", "value": v, "unit": "V-cycles/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * s_full, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, full_sides),
+        "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": cores},
+        "e2e": {"value": v, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, sides):
+    return {
+        "workload": "2D unit-square jittered cloud %dx%d = %d nodes, manufactured Dirichlet Poisson, %d-level V-cycle (sides %s), "
+                    "fine polyDeg %d / coarse polyDeg 3, nu=5, omega=1.4" % (args.side, args.side, args.side ** 2, len(sides), sides, args.fine_poly),
+        "smoother": args.smoother, "l2": "inputs larger than L2 (finest operator alone is >1 GB vs 126 MB L2)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=2000, help="finest lattice side (2000 -> 4M nodes)")
+    ap.add_argument("--levels", type=int, default=None, help="number of levels (default: coarsen until the side is <= 16)")
+    ap.add_argument("--fine-poly", type=int, default=4)
+    ap.add_argument("--smoother", default="multicolour", choices=["multicolour", "lexicographic"])
+    ap.add_argument("--cpu-side", type=int, default=500, help="finest lattice side of the bounded CPU sample")
+    ap.add_argument("--cpu-cycles", type=int, default=3)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-lex", action="store_true")
+    ap.add_argument("--skip-solve", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    from meshlessmultigridpoisson_b200 import build, capi
+    from meshlessmultigridpoisson_b200.problems import make_hierarchy
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solve path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    build.build()
+    capi.load()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sides = level_sides(args.side, args.levels)
+    t0 = time.time()
+    mg = make_hierarchy(sides, "dirichlet", args.fine_poly, device=local)
+    mg.sync()
+    setup_s = time.time() - t0
+    fast = args.smoother == "multicolour"
+    mg.set_smoother(capi.MULTICOLOUR if fast else capi.LEXICOGRAPHIC)
+    mg.set_arithmetic(capi.ARITH_FAST if fast else capi.ARITH_REFERENCE_ORDER)
+    fine = mg.grid(-1)
+    A = fine.A_size
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps, CUDA events on the solver's stream
+    mg.vCycle(args.warmup)
+    sampler = ClockSampler(local)
+    barrier()
+    mg.enable_timers(True)
+    mg.reset_timers()
+    launches0 = mg.launch_count()
+    c0 = sampler.mark()
+    ms = mg.time_vcycles(args.steps)
+    c1 = sampler.mark()
+    barrier()
+    clocks = sampler.stop(c0, c1)
+    gpu_launches = mg.launch_count() - launches0
+    tm_fine = mg.timers(len(sides) - 1)
+    tm_all = mg.timers(-1)
+    mg.enable_timers(False)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step          # every rank runs the same per-GPU workload (weak scaling, replicas)
+
+    # ---- roofline of the dominant kernel: finest-level SOR sweep
+    peak, peak_src = measured_peaks()
+    sor = tm_fine["sor"]
+    achieved = sor["bytes"] / (sor["ms"] * 1e-3) / 1e9 if sor["ms"] > 0 else 0.0
+    shares = {k: round(v["ms"] / max(1e-9, sum(x["ms"] for x in tm_all.values())), 4) for k, v in tm_all.items()}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "k_sor_mc (finest level, one launch per colour)" if fast else "k_sor_lex_exact (finest level)",
+                "peak_source": peak_src, "bytes_per_launch_set": sor["bytes"] // max(1, sor["launches"]),
+                "sor_share_of_step": shares.get("sor"), "class_shares": shares,
+                "whole_cycle_GBps": algorithmic_bytes_per_cycle(sides, args.fine_poly) / (ms_per_step * 1e-3) / 1e9}
+
+    # ---- end to end through the C-ABI with host buffers (pinned), copies inside the timed region
+    src = torch.empty(A, dtype=torch.float64).pin_memory().numpy()
+    val = torch.empty(A, dtype=torch.float64).pin_memory().numpy()
+    src[:] = fine.source_
+    val[:] = fine.values_
+    for _ in range(2):
+        fine.source_ = src; fine.values_ = val; mg.vCycle(1); val[:] = fine.values_
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fine.source_ = src            # H2D
+        fine.values_ = val            # H2D
+        mg.vCycle(1)
+        val[:] = fine.values_         # D2H
+        res = mg.residuals_[-1:]      # D2H of the step's residual entry
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world / e2e_s, "unit": "V-cycles/s", "h2d_bytes_per_step": 16 * A, "d2h_bytes_per_step": 8 * A + 8}
+
+    line = {
+        "metric": "vcycles_per_s", "value": value, "unit": "V-cycles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, sides), "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+        "setup_s": setup_s,
+    }
+
+    if rank == 0:
+        # ---- solve to 1e-8 from a zero guess
+        if not args.skip_solve:
+            fine.values_ = np.zeros(A)
+            barrier()
+            t0 = time.perf_counter()
+            n, r = mg.solve(TOL, 400)
+            mg.sync()
+            line["solve"] = {"tol": TOL, "cycles": n, "seconds": time.perf_counter() - t0, "final_residual": r, "mode": args.smoother}
+        # ---- the reference-faithful mode, reported separately
+        if fast and not args.skip_lex:
+            mg.set_smoother(capi.LEXICOGRAPHIC)
+            mg.set_arithmetic(capi.ARITH_REFERENCE_ORDER)
+            fine.values_ = np.zeros(A)
+            mg.vCycle(1)
+            lex_ms = mg.time_vcycles(2) / 2
+            nl, _ = fine.lex_levels() if args.side <= 1000 else (None, None)
+            line["lexicographic"] = {"value": 1e3 / lex_ms, "unit": "V-cycles/s", "ms_per_step": lex_ms, "dag_levels_finest": nl,
+                                     "note": "dependency-DAG sweep, reference-order row sums; bounded by DAG depth x L2 latency, not HBM"}
+        # ---- CPU baseline beside it (bounded sample)
+        if not args.skip_cpu:
+            cores = os.cpu_count() or 1
+            r = run_cpu_oracle(args.cpu_side, None, args.fine_poly, args.cpu_cycles, cores)
+            scale = algorithmic_bytes_per_cycle(r["sides"], args.fine_poly) / algorithmic_bytes_per_cycle(sides, args.fine_poly)
+            s_full = r["s_per_cycle"] / scale
+            line["cpu_baseline"] = {
+                "value": 1.0 / s_full, "unit": "V-cycles/s", "cores": 1, "kind": "port", "host_cores": cores,
+                "sample": "CPU oracle, lexicographic SOR, %d V-cycles on a %dx%d-side hierarchy %s (%.3f s/cycle measured), scaled by algorithmic "
+                          "bytes x%.4g to the %dx%d workload; set-up used %d threads (%.1f s, untimed)"
+                          % (args.cpu_cycles, args.cpu_side, args.cpu_side, r["sides"], r["s_per_cycle"], 1 / scale, args.side, args.side, cores, r["setup_s"]),
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

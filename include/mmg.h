@@ -140,7 +140,7 @@ int mmg_solver_solve(mmg_solver* s, double tol, int max_cycles, int extra_bound_
 int mmg_solver_sync(mmg_solver* s);
 /* measurement hooks: CUDA-event time (ms) and launch counts accumulated per kernel class since the last reset */
 int mmg_solver_enable_timers(mmg_solver* s, int on);
-int mmg_solver_get_timers(mmg_solver* s, double* ms, int64_t* launches, int64_t* bytes);
+int mmg_solver_get_timers(mmg_solver* s, int level, double* ms, int64_t* launches, int64_t* bytes); /* level -1 = all levels; arrays of MMG_T_COUNT */
 int mmg_solver_reset_timers(mmg_solver* s);
 int mmg_solver_launch_count(mmg_solver* s, int64_t* launches);                     /* kernels launched by this solver so far */
 /* CUDA-event timed V-cycles on the solver's stream: runs n cycles, returns elapsed device ms */

@@ -102,7 +102,7 @@ SIGNATURES = {
     "mmg_solver_solve": [_vp, _d, _i, _i, C.POINTER(_i), C.POINTER(_d)],
     "mmg_solver_sync": [_vp],
     "mmg_solver_enable_timers": [_vp, _i],
-    "mmg_solver_get_timers": [_vp, _dp, _lp, _lp],
+    "mmg_solver_get_timers": [_vp, _i, _dp, _lp, _lp],
     "mmg_solver_reset_timers": [_vp],
     "mmg_solver_launch_count": [_vp, C.POINTER(C.c_int64)],
     "mmg_solver_time_vcycles": [_vp, _i, C.POINTER(_d)],
@@ -458,9 +458,10 @@ class Multigrid:
     def reset_timers(self):
         _ck(self.L, self.L.mmg_solver_reset_timers(self.h))
 
-    def timers(self):
+    def timers(self, level=-1):
+        """CUDA-event time, launch count and algorithmic bytes per kernel class (level -1 = all levels)."""
         ms, ln, by = np.zeros(T_COUNT), np.zeros(T_COUNT, np.int64), np.zeros(T_COUNT, np.int64)
-        _ck(self.L, self.L.mmg_solver_get_timers(self.h, ms, ln, by))
+        _ck(self.L, self.L.mmg_solver_get_timers(self.h, level, ms, ln, by))
         names = ["sor", "residual", "restrict", "prolong", "other"]
         return {k: dict(ms=float(ms[i]), launches=int(ln[i]), bytes=int(by[i])) for i, k in enumerate(names)}
 

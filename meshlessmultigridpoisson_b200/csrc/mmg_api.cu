@@ -556,6 +556,7 @@ int mmg_solver_add_grid(mmg_solver* s, mmg_grid* g) {
   gr->timers = &so.timers;
   so.grids.push_back(gr);
   std::sort(so.grids.begin(), so.grids.end(), [](Grid* a, Grid* b) { return a->n != b->n ? a->n < b->n : a < b; });  // multigrid.cpp:116-122
+  for (size_t i = 0; i < so.grids.size(); i++) so.grids[i]->level = (int)i;
   for (HybMatrix* m : so.restrict_) delete m;
   for (HybMatrix* m : so.prolong_) delete m;
   so.restrict_.assign(so.grids.size(), nullptr);
@@ -800,16 +801,20 @@ int mmg_solver_enable_timers(mmg_solver* s, int on) {
   S(s).timers.on = on != 0;
   API_END
 }
-int mmg_solver_get_timers(mmg_solver* s, double* ms, int64_t* launches, int64_t* bytes) {
+int mmg_solver_get_timers(mmg_solver* s, int level, double* ms, int64_t* launches, int64_t* bytes) {
   API_BEGIN
   NEED(s);
   Solver& so = S(s);
+  MMG_REQUIRE(level >= -1 && level < kMaxLevels, MMG_ERR_ARG, "timers: level out of range (-1 = all levels)");
   if (so.stream) MMG_CUDA(cudaStreamSynchronize(so.stream));
   timers_collect(so.timers);
   for (int i = 0; i < MMG_T_COUNT; i++) {
-    if (ms) ms[i] = so.timers.ms[i];
-    if (launches) launches[i] = so.timers.launches[i];
-    if (bytes) bytes[i] = so.timers.bytes[i];
+    double m = 0; int64_t l = 0, b = 0;
+    for (int lv = 0; lv < kMaxLevels; lv++)
+      if (level < 0 || lv == level) { m += so.timers.ms[lv][i]; l += so.timers.launches[lv][i]; b += so.timers.bytes[lv][i]; }
+    if (ms) ms[i] = m;
+    if (launches) launches[i] = l;
+    if (bytes) bytes[i] = b;
   }
   API_END
 }
@@ -819,7 +824,8 @@ int mmg_solver_reset_timers(mmg_solver* s) {
   Solver& so = S(s);
   if (so.stream) MMG_CUDA(cudaStreamSynchronize(so.stream));
   timers_collect(so.timers);
-  for (int i = 0; i < MMG_T_COUNT; i++) { so.timers.ms[i] = 0; so.timers.launches[i] = 0; so.timers.bytes[i] = 0; }
+  for (int lv = 0; lv < kMaxLevels; lv++)
+    for (int i = 0; i < MMG_T_COUNT; i++) { so.timers.ms[lv][i] = 0; so.timers.launches[lv][i] = 0; so.timers.bytes[lv][i] = 0; }
   API_END
 }
 int mmg_solver_launch_count(mmg_solver* s, int64_t* launches) {

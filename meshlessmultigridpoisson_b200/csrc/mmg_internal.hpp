@@ -126,18 +126,20 @@ struct Boundary {
   std::vector<double> vals;
 };
 
+constexpr int kMaxLevels = 24;
 struct Timers {
   bool on = false;
-  double ms[MMG_T_COUNT] = {0, 0, 0, 0, 0};
-  int64_t launches[MMG_T_COUNT] = {0, 0, 0, 0, 0};
-  int64_t bytes[MMG_T_COUNT] = {0, 0, 0, 0, 0};
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+  double ms[kMaxLevels][MMG_T_COUNT] = {};
+  int64_t launches[kMaxLevels][MMG_T_COUNT] = {};
+  int64_t bytes[kMaxLevels][MMG_T_COUNT] = {};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;   // (level*MMG_T_COUNT+class, events)
   std::vector<cudaEvent_t> pool;
   int64_t total_launches = 0;
 };
 
 struct Grid {
   int device = 0;
+  int level = 0;    // position inside the owning solver (0 = coarsest); only used to bucket the timers
   int n = 0;        // laplaceMatSize_
   int A = 0;        // rows of laplaceMat_ (n, or n+1 with any Neumann boundary)
   bool neumann = false, implicit = false;
@@ -223,7 +225,7 @@ void asm_build_interp(Grid& base, Grid& target, int polyDeg, HybMatrix& out);
 // ---- timers ---------------------------------------------------------------------------------------
 struct TimedScope {
   Timers* t; int cls; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr;
-  TimedScope(Timers* t_, int cls_, cudaStream_t s_, int64_t bytes, int launches = 1);
+  TimedScope(Grid& g, int cls_, int64_t bytes, int launches = 1);
   ~TimedScope();
 };
 void timers_collect(Timers& t);

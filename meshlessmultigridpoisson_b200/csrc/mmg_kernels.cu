@@ -667,11 +667,13 @@ constexpr int kRegBlocks = 296;
 // ------------------------------------------------------------------------------------------------
 // timers
 // ------------------------------------------------------------------------------------------------
-TimedScope::TimedScope(Timers* t_, int cls_, cudaStream_t s_, int64_t bytes, int launches) : t(t_), cls(cls_), s(s_) {
+TimedScope::TimedScope(Grid& g, int cls_, int64_t bytes, int launches) : t(g.timers), cls(cls_), s(g.stream) {
   if (!t) return;
+  const int lv = g.level < kMaxLevels ? g.level : kMaxLevels - 1;
+  cls = lv * MMG_T_COUNT + cls_;
   t->total_launches += launches;
-  t->launches[cls] += launches;
-  t->bytes[cls] += bytes;
+  t->launches[lv][cls_] += launches;
+  t->bytes[lv][cls_] += bytes;
   if (!t->on) return;
   auto get = [&]() {
     cudaEvent_t e;
@@ -692,7 +694,7 @@ void timers_collect(Timers& t) {
     float ms = 0;
     cudaEventSynchronize(p.second.second);
     cudaEventElapsedTime(&ms, p.second.first, p.second.second);
-    t.ms[p.first] += ms;
+    t.ms[p.first / MMG_T_COUNT][p.first % MMG_T_COUNT] += ms;
     t.pool.push_back(p.second.first);
     t.pool.push_back(p.second.second);
   }
@@ -837,7 +839,7 @@ static void residual_impl(Grid& g, double* r_out, double* ratio_dev) {
   double* reg_partial = g.partials.p + 2 * maxblocks;
   int nb = 0;
   {
-    TimedScope ts(g.timers, MMG_T_RESIDUAL, g.stream, L.matrix_bytes() + (int64_t)g.A * 24, 2 + (L.reg_row >= 0));
+    TimedScope ts(g, MMG_T_RESIDUAL, L.matrix_bytes() + (int64_t)g.A * 24, 2 + (L.reg_row >= 0));
     launch_spmv(L, g.x.p, g.b.p, r_out, g.rowflag.p, OP_RESID, 0, 0, norm_partial, &nb, g.device, g.stream, g.exact);
     const int n_reg = launch_regdot(g, g.x.p, reg_partial);
     k_finish_residual<<<1, kBlock, 0, g.stream>>>(norm_partial, nb, reg_partial, n_reg, L.reg_row, L.reg_diag, g.x.p, g.b.p, r_out, ratio_dev);
@@ -852,7 +854,7 @@ void op_bound_eval_neumann(Grid& g) {
   if (g.neu_pts.n == 0) return;
   MMG_REQUIRE(g.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
   const int sms = sm_count_of(g.device);
-  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.neu_pts.n * (12 * g.Lap.W + 24));
+  TimedScope ts(g, MMG_T_OTHER, (int64_t)g.neu_pts.n * (12 * g.Lap.W + 24));
   if (g.exact) {
     k_bound_eval_exact<<<grid_for((int)g.neu_pts.n, 32, sms), kBlock, 0, g.stream>>>(g.Lap.view(), g.neu_pts.p, (int)g.neu_pts.n, g.b.p, g.x.p);
   } else {
@@ -866,13 +868,13 @@ void op_bound_eval_neumann(Grid& g) {
 
 void op_boundary_op(Grid& g, int coarse) {  // grid.cpp:42-51
   if (g.dir_pts.n == 0) return;
-  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.dir_pts.n * 20);
+  TimedScope ts(g, MMG_T_OTHER, (int64_t)g.dir_pts.n * 20);
   k_scatter<<<((int)g.dir_pts.n + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.dir_pts.p, g.dir_vals.p, (int)g.dir_pts.n, g.x.p, coarse);
   MMG_CUDA(cudaGetLastError());
 }
 
 void op_modify_coeff_neumann(Grid& g, int coarse) {  // grid.cpp:62-72
-  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.neu_pts.n * 20 + 8, 1 + (g.neu_pts.n ? 1 : 0));
+  TimedScope ts(g, MMG_T_OTHER, (int64_t)g.neu_pts.n * 20 + 8, 1 + (g.neu_pts.n ? 1 : 0));
   if (g.neu_pts.n) k_scatter<<<((int)g.neu_pts.n + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.neu_pts.p, g.neu_vals.p, (int)g.neu_pts.n, g.b.p, coarse);
   k_set_one<<<1, 1, 0, g.stream>>>(g.b.p, (int)g.b.n - 1, 0.0);
   MMG_CUDA(cudaGetLastError());
@@ -880,31 +882,31 @@ void op_modify_coeff_neumann(Grid& g, int coarse) {  // grid.cpp:62-72
 
 void op_fix_vector_bound_coarse(Grid& g, double* vec_dev) {  // grid.cpp:197-205
   if (g.dir_pts.n == 0) return;
-  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.dir_pts.n * 12);
+  TimedScope ts(g, MMG_T_OTHER, (int64_t)g.dir_pts.n * 12);
   k_scatter<<<((int)g.dir_pts.n + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.dir_pts.p, nullptr, (int)g.dir_pts.n, vec_dev, 1);
   MMG_CUDA(cudaGetLastError());
 }
 
 void op_zero_values(Grid& g) {
-  TimedScope ts(g.timers, MMG_T_OTHER, g.stream, (int64_t)g.A * 8);
+  TimedScope ts(g, MMG_T_OTHER, (int64_t)g.A * 8);
   g.x.zero(g.stream);
 }
 
 void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class) {
-  TimedScope ts(ctx.timers, timer_class, ctx.stream, M.matrix_bytes() + (int64_t)M.rows * 8 + (int64_t)M.cols * 8);
+  TimedScope ts(ctx, timer_class, M.matrix_bytes() + (int64_t)M.rows * 8 + (int64_t)M.cols * 8);
   launch_spmv(M, x_dev, nullptr, y_dev, nullptr, OP_SPMV, 0, 0, nullptr, nullptr, ctx.device, ctx.stream, ctx.exact);
 }
 
 void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fine_res_dev) {
   MMG_REQUIRE(R.rows == coarse.n && R.cols == fine.n, MMG_ERR_STATE, "restriction matrix shape does not match the grids");
   {
-    TimedScope ts(fine.timers, MMG_T_RESTRICT, fine.stream, R.matrix_bytes() + (int64_t)coarse.n * 8 + (int64_t)fine.n * 8);
+    TimedScope ts(fine, MMG_T_RESTRICT, R.matrix_bytes() + (int64_t)coarse.n * 8 + (int64_t)fine.n * 8);
     // fix_vector_bound_coarse on the coarse source and, if the FINE grid is Neumann, modify_coeff_neumann("coarse"):
     // both are masks on the output rows (multigrid.cpp:82-86)
     launch_spmv(R, fine_res_dev, nullptr, coarse.b.p, coarse.rowflag.p, OP_RESTRICT, 1, fine.neumann ? 1 : 0, nullptr, nullptr, fine.device, fine.stream, fine.exact);
   }
   if (fine.neumann) {  // source_(rows-1)=0 (multigrid.cpp:84) and the same store inside modify_coeff_neumann (grid.cpp:71)
-    TimedScope ts(fine.timers, MMG_T_OTHER, fine.stream, 8);
+    TimedScope ts(fine, MMG_T_OTHER, 8);
     k_set_one<<<1, 1, 0, fine.stream>>>(coarse.b.p, (int)coarse.b.n - 1, 0.0);
     MMG_CUDA(cudaGetLastError());
   }
@@ -912,7 +914,7 @@ void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fin
 
 void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P) {
   MMG_REQUIRE(P.rows == fine.n && P.cols == coarse.n, MMG_ERR_STATE, "prolongation matrix shape does not match the grids");
-  TimedScope ts(fine.timers, MMG_T_PROLONG, fine.stream, P.matrix_bytes() + (int64_t)fine.n * 16 + (int64_t)coarse.n * 8);
+  TimedScope ts(fine, MMG_T_PROLONG, P.matrix_bytes() + (int64_t)fine.n * 16 + (int64_t)coarse.n * 8);
   launch_spmv(P, coarse.x.p, nullptr, fine.x.p, fine.rowflag.p, OP_PROLONG, fine.neumann ? 0 : 1, 0, nullptr, nullptr, fine.device, fine.stream, fine.exact);
 }
 
@@ -1007,7 +1009,7 @@ void op_sor(Grid& g, int smoother) {
   for (int it = 0; it < g.props.iters; it++) {
     {
       const int launches = smoother == MMG_SMOOTHER_MULTICOLOUR ? g.n_colours + 1 : 2 + (L.reg_row >= 0 ? 2 : 0);
-      TimedScope ts(g.timers, MMG_T_SOR, g.stream, L.matrix_bytes() + (int64_t)g.A * 28, launches);
+      TimedScope ts(g, MMG_T_SOR, L.matrix_bytes() + (int64_t)g.A * 28, launches);
       if (smoother == MMG_SMOOTHER_MULTICOLOUR) sor_mc_sweep(g); else sor_lex_sweep(g);
     }
     op_bound_eval_neumann(g);  // grid.cpp:144
