@@ -77,6 +77,7 @@ int mmg_grid_modify_coeff_neumann(mmg_grid* g, int coarse);                     
 int mmg_grid_push_inhomog_to_rhs(mmg_grid* g);                                     /* Grid::push_inhomog_to_rhs grid.cpp:664-685 */
 int mmg_grid_boundary_op(mmg_grid* g, int coarse);                                 /* Grid::boundaryOp grid.cpp:42-51 */
 int mmg_grid_bound_eval_neumann(mmg_grid* g);                                      /* Grid::bound_eval_neumann grid.cpp:73-103 */
+int mmg_grid_set_props(mmg_grid* g, const mmg_props* props);                       /* Grid::properties_ (omega, iters) grid.h:30 */
 int mmg_grid_set_arithmetic(mmg_grid* g, int arithmetic);                          /* MMG_ARITH_*: no reference counterpart (the reference has one order) */
 int mmg_grid_sor(mmg_grid* g, int smoother);                                       /* Grid::sor(laplaceMat_, values_, &source_) grid.cpp:104-146 */
 int mmg_grid_residual(mmg_grid* g, double* out);                                   /* Grid::residual grid.cpp:147-151 (A entries) */
@@ -129,6 +130,7 @@ int mmg_solver_set_smoother(mmg_solver* s, int smoother);                       
 int mmg_solver_restrict(mmg_solver* s, int level);                                 /* source_{i-1} = R_i * residual_i + masks, multigrid.cpp:81-86 */
 int mmg_solver_prolong_correct(mmg_solver* s, int level);                          /* values_i += P_{i-1} * values_{i-1}, multigrid.cpp:102-106 */
 int mmg_solver_coarse_solve(mmg_solver* s);                                        /* coarsest level: zero guess + 2 sor calls, multigrid.cpp:92-95 */
+int mmg_solver_set_omega(mmg_solver* s, double omega);                             /* properties_.omega of every grid (gridclasses.hpp:12) */
 int mmg_solver_set_arithmetic(mmg_solver* s, int arithmetic);                      /* MMG_ARITH_* for every grid of the solver */
 int mmg_solver_vcycle(mmg_solver* s, int n_cycles);                                /* Multigrid::vCycle multigrid.cpp:62-110, n times, no host sync inside */
 int mmg_solver_residual(mmg_solver* s, double* out);                               /* Multigrid::residual multigrid.cpp:112-115 */

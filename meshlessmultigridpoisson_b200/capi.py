@@ -57,6 +57,7 @@ SIGNATURES = {
     "mmg_grid_push_inhomog_to_rhs": [_vp],
     "mmg_grid_boundary_op": [_vp, _i],
     "mmg_grid_bound_eval_neumann": [_vp],
+    "mmg_grid_set_props": [_vp, C.POINTER(MmgProps)],
     "mmg_grid_set_arithmetic": [_vp, _i],
     "mmg_grid_sor": [_vp, _i],
     "mmg_grid_residual": [_vp, _dp],
@@ -94,6 +95,7 @@ SIGNATURES = {
     "mmg_solver_restrict": [_vp, _i],
     "mmg_solver_prolong_correct": [_vp, _i],
     "mmg_solver_coarse_solve": [_vp],
+    "mmg_solver_set_omega": [_vp, _d],
     "mmg_solver_set_arithmetic": [_vp, _i],
     "mmg_solver_vcycle": [_vp, _i],
     "mmg_solver_residual": [_vp, C.POINTER(_d)],
@@ -305,6 +307,10 @@ class Grid:
     def bound_eval_neumann(self):
         _ck(self.L, self.L.mmg_grid_bound_eval_neumann(self.h))
 
+    def set_props(self, properties):
+        p = MmgProps(properties["rbfExp"], properties["polyDeg"], properties["stencilSize"], properties["iters"], properties["omega"])
+        _ck(self.L, self.L.mmg_grid_set_props(self.h, C.byref(p)))
+
     def set_arithmetic(self, arithmetic):
         _ck(self.L, self.L.mmg_grid_set_arithmetic(self.h, arithmetic))
 
@@ -415,6 +421,9 @@ class Multigrid:
 
     def set_smoother(self, smoother):
         _ck(self.L, self.L.mmg_solver_set_smoother(self.h, smoother))
+
+    def set_omega(self, omega):
+        _ck(self.L, self.L.mmg_solver_set_omega(self.h, omega))
 
     def set_arithmetic(self, arithmetic):
         _ck(self.L, self.L.mmg_solver_set_arithmetic(self.h, arithmetic))

@@ -324,6 +324,15 @@ int mmg_grid_bound_eval_neumann(mmg_grid* g) {
   op_bound_eval_neumann(G(g));
   API_END
 }
+int mmg_grid_set_props(mmg_grid* g, const mmg_props* props) {
+  API_BEGIN
+  NEED(g); NEED(props);
+  MMG_REQUIRE(props->polyDeg == G(g).props.polyDeg && props->stencilSize == G(g).props.stencilSize && props->rbfExp == G(g).props.rbfExp, MMG_ERR_ARG,
+              "set_props: only omega and iters may change once the grid exists (the operators are built from the rest)");
+  MMG_REQUIRE(props->iters >= 0, MMG_ERR_ARG, "set_props: iters must be >= 0");
+  G(g).props = *props;
+  API_END
+}
 int mmg_grid_set_arithmetic(mmg_grid* g, int arithmetic) {
   API_BEGIN
   NEED(g);
@@ -695,6 +704,12 @@ int mmg_solver_coarse_solve(mmg_solver* s) {
   op_sor(c, so.smoother);
   MMG_CUDA(cudaStreamSynchronize(so.stream));
   solver_check_abort(so);
+  API_END
+}
+int mmg_solver_set_omega(mmg_solver* s, double omega) {
+  API_BEGIN
+  NEED(s);
+  for (Grid* g : S(s).grids) g->props.omega = omega;
   API_END
 }
 int mmg_solver_set_arithmetic(mmg_solver* s, int arithmetic) {

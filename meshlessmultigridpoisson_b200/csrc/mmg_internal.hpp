@@ -160,6 +160,7 @@ struct Grid {
   bool have_laplacian = false;
 
   // device state
+  DevBuf<double> xs;                     // versioned vectors of the sweep-pipelined lexicographic kernel
   DevBuf<double> x, x_alt, b, r;         // values_, sweep scratch, source_, residual scratch (A entries)
   DevBuf<double> px, py;                 // points_
   DevBuf<unsigned char> rowflag;         // bcFlags_ per row as uint8 (A entries; regularisation row = 0)

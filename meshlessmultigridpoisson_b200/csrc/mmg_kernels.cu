@@ -481,6 +481,22 @@ __global__ void __launch_bounds__(32) k_regdot_exact(const int* __restrict__ col
   if (lane == 0) partial[0] = s;
 }
 
+// s <- s - p_l for lanes l = 0..cnt-1 in lane order.  Lanes >= cnt hold 0.0 (x - 0.0 == x bit for bit), so whole
+// groups of 8 are folded without per-element predicates: the shuffles hoist, the DSUB chain is the only dependency.
+__device__ __forceinline__ double fold_sub32(double s, double p, int cnt) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; g8++) {
+    if (cnt > g8 * 8) {
+      double q[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) q[l] = __shfl_sync(0xffffffffu, p, g8 * 8 + l);
+#pragma unroll
+      for (int l = 0; l < 8; l++) s = __dsub_rn(s, q[l]);
+    }
+  }
+  return s;
+}
+
 // Lexicographic sweep, reference-order arithmetic: warp per row; products wait on their dependencies
 // in parallel, then the row sum is folded in ascending column order.
 template <int T>
@@ -512,17 +528,18 @@ __global__ void __launch_bounds__(kBlock) k_sor_lex_exact(HybView A, const unsig
         else { pv[t] = a; pc[t] = col; pend |= 1u << t; }
       }
     }
-    const double diag = v[0];
+    const double wd = omega / v[0];
+    const double bi = b[row];
+    const double xo_term = __dmul_rn(1 - omega, x_old[row]);
     unsigned spins = 0;
     bool aborted = false;
     while (__any_sync(0xffffffffu, pend != 0)) {
+      double xv[T];
 #pragma unroll
-      for (int t = 0; t < T; t++) {
-        if (pend & (1u << t)) {
-          const double xv = ld_relaxed(x_new + pc[t]);
-          if (!is_sentinel(xv)) { prod[t] = __dmul_rn(pv[t], xv); pend &= ~(1u << t); }
-        }
-      }
+      for (int t = 0; t < T; t++) xv[t] = (pend & (1u << t)) ? ld_relaxed(x_new + pc[t]) : 0.0;
+#pragma unroll
+      for (int t = 0; t < T; t++)
+        if ((pend & (1u << t)) && !is_sentinel(xv[t])) { prod[t] = __dmul_rn(pv[t], xv[t]); pend &= ~(1u << t); }
       if ((++spins & 0xff) == 0) {
         if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
       }
@@ -530,12 +547,7 @@ __global__ void __launch_bounds__(kBlock) k_sor_lex_exact(HybView A, const unsig
     if (aborted) { if (lane == 0) st_relaxed(x_new + row, 0.0); return; }
     double s = 0.0;                          // x_i = 0; x_i -= a_ij * v_j, ascending j (grid.cpp:122-136)
 #pragma unroll
-    for (int t = 0; t < T; t++) {
-      const int cnt = min(32, m - 1 - t * 32);
-#pragma unroll
-      for (int l = 0; l < 32; l++)
-        if (l < cnt) s = __dsub_rn(s, __shfl_sync(0xffffffffu, prod[t], l));
-    }
+    for (int t = 0; t < T; t++) s = fold_sub32(s, prod[t], m - 1 - t * 32);
     if (len > A.W) {  // spill rows: blocking in-order tail
       const int o = ovf_find(A, row);
       const int e = A.ovf_ptr[o + 1];
@@ -555,19 +567,103 @@ __global__ void __launch_bounds__(kBlock) k_sor_lex_exact(HybView A, const unsig
           }
           p = __dmul_rn(A.ovf_val[k], xv);
         }
-        const int cnt = min(32, e - base);
-#pragma unroll
-        for (int l = 0; l < 32; l++)
-          if (l < cnt) s = __dsub_rn(s, __shfl_sync(0xffffffffu, p, l));
+        s = fold_sub32(s, p, e - base);
       }
     }
     if (lane == 0) {                         // x+=b; x*=w/d; x+=(1-w)x_old (grid.cpp:137-141)
-      double xi = __dadd_rn(s, b[row]);
-      xi = __dmul_rn(xi, omega / diag);
-      xi = __dadd_rn(xi, __dmul_rn(1 - omega, x_old[row]));
+      double xi = __dadd_rn(s, bi);
+      xi = __dmul_rn(xi, wd);
+      xi = __dadd_rn(xi, xo_term);
       st_relaxed(x_new + row, xi);
     }
   }
+}
+
+// Sweep-pipelined lexicographic SOR for grids without Neumann rows (no global reduction between sweeps).
+// All `iters` sweeps run inside ONE cooperative launch on versioned vectors xs[0..iters] (xs[0] = input,
+// xs[s] = state after sweep s; swept rows start as the sentinel, skipped rows as their constant value).
+// Row i of sweep s reads xs[s][c] for c<i and xs[s-1][c] for c>=i, exactly the values the sequential
+// in-place sweeps see, so sweep s+1 trails sweep s by one matrix bandwidth instead of a full sweep.
+// Warps are dealt to sweeps round-robin (warp w -> sweep 1 + w % iters) and walk their rows in increasing
+// order; ordering tasks by key = row + sweep * D (D > bandwidth) shows every dependency has a smaller key and
+// every warp visits its tasks in increasing key order, so the smallest unfinished task can always run:
+// no deadlock as long as all CTAs are resident (cooperative launch).  Reference-order arithmetic.
+template <int T>
+__global__ void __launch_bounds__(kBlock) k_sor_lex_pipe(HybView A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b, double* xs,
+                                                         size_t stride, int iters, double omega, int* abort_flag, long long timeout_cycles,
+                                                         unsigned sleep_ns) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int sweep = 1 + warp % iters;
+  const int q = warp / iters, Q = nwarps / iters;
+  if (q >= Q) return;                              // leftover warps when nwarps % iters != 0
+  const double* x_old = xs + (size_t)(sweep - 1) * stride;
+  double* x_new = xs + (size_t)sweep * stride;
+  const long long t_start = clock64();
+  for (int row = q; row < A.rows; row += Q) {
+    if (rowflag[row] != 0) continue;
+    const int len = A.len[row];
+    const double* __restrict__ v = row_val(A, row);
+    const int* __restrict__ c = row_col(A, row);
+    const int m = len < A.W ? len : A.W;
+    double prod[T];
+    double pv[T];
+    const double* pp[T];
+    unsigned pend = 0;
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      const int k = 1 + lane + t * 32;             // slot 0 is the diagonal
+      prod[t] = 0.0; pv[t] = 0.0; pp[t] = nullptr;
+      if (k < m) {
+        pv[t] = v[k];
+        const int col = c[k];
+        pp[t] = (col > row ? x_old : x_new) + col;
+        pend |= 1u << t;
+      }
+    }
+    const double wd = omega / v[0];            // off the critical path: known before any dependency resolves
+    const double bi = b[row];
+    double xo = 0.0;
+    bool need_xo = lane == 0;
+    unsigned spins = 0;
+    bool aborted = false;
+    while (true) {
+      double xv[T];
+#pragma unroll
+      for (int t = 0; t < T; t++) xv[t] = (pend & (1u << t)) ? ld_relaxed(pp[t]) : 0.0;   // all polls in flight together
+      if (need_xo) { xo = ld_relaxed(x_old + row); need_xo = is_sentinel(xo); }
+#pragma unroll
+      for (int t = 0; t < T; t++)
+        if ((pend & (1u << t)) && !is_sentinel(xv[t])) { prod[t] = __dmul_rn(pv[t], xv[t]); pend &= ~(1u << t); }
+      if (!__any_sync(0xffffffffu, pend != 0 || need_xo)) break;
+      if (sleep_ns) __nanosleep(sleep_ns);
+      if ((++spins & 0xff) == 0) {
+        if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
+      }
+    }
+    if (aborted) { if (lane == 0) st_relaxed(x_new + row, 0.0); return; }
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < T; t++) s = fold_sub32(s, prod[t], m - 1 - t * 32);
+    if (lane == 0) {
+      double xi = __dadd_rn(s, bi);
+      xi = __dmul_rn(xi, wd);
+      xi = __dadd_rn(xi, __dmul_rn(1 - omega, xo));
+      st_relaxed(x_new + row, xi);
+    }
+  }
+}
+
+// xs[0] = x; xs[s>=1][i] = skipped(i) ? x[i] : sentinel
+__global__ void __launch_bounds__(kBlock) k_pipe_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x, double* xs, size_t stride,
+                                                      int iters, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double xi = x[i];
+  const bool skipped = rowflag[i] != 0;
+  xs[i] = xi;
+  for (int s = 1; s <= iters; s++) xs[(size_t)s * stride + i] = skipped ? xi : __longlong_as_double((long long)kSentinelBits);
 }
 
 __global__ void __launch_bounds__(kBlock) k_sor_mc_exact(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
@@ -919,15 +1015,60 @@ void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P) {
 }
 
 // ---- SOR -----------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int lex_block_cap(int sms) { static int v = -2; if (v == -2) v = env_int("MMG_LEX_BLOCKS", 0); return v > 0 ? v : 2 * sms; }
+static unsigned lex_sleep_ns() { static int v = -2; if (v == -2) v = env_int("MMG_LEX_SLEEP_NS", 0); return (unsigned)v; }
+
+template <int T>
+static void launch_lex_pipe(Grid& g) {
+  const int iters = g.props.iters;
+  const size_t stride = ((size_t)g.A + 63) / 64 * 64;
+  if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
+  k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
+  MMG_CUDA(cudaGetLastError());
+  int blocks_per_sm = 0;
+  MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_lex_pipe<T>, kBlock, 0));
+  const int sms = sm_count_of(g.device);
+  int blocks = std::min(blocks_per_sm * sms, lex_block_cap(sms) * std::min(iters, 3));
+  const int need = grid_for(g.Lap.rows, 32, 1 << 20) * iters;
+  if (blocks > need) blocks = need;
+  if (blocks * (kBlock / 32) < iters) blocks = (iters + kBlock / 32 - 1) / (kBlock / 32);
+  HybView A = g.Lap.view();
+  const unsigned char* rf = g.rowflag.p;
+  const double* b = g.b.p;
+  double* xs = g.xs.p;
+  size_t st = stride;
+  int it = iters;
+  double omega = g.props.omega;
+  int* abortp = g.abort_flag.p;
+  long long timeout = 6000000000ll;
+  unsigned sleep_ns = lex_sleep_ns();
+  void* args[] = {&A, &rf, &b, &xs, &st, &it, &omega, &abortp, &timeout, &sleep_ns};
+  MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_lex_pipe<T>, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+  MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
+}
+
+// all props.iters lexicographic sweeps of a grid without Neumann rows in one pipelined launch
+static bool sor_lex_pipelined(Grid& g) {
+  const int Te = (g.Lap.W - 1 + 31) / 32;
+  if (Te <= 1) launch_lex_pipe<1>(g);
+  else if (Te <= 2) launch_lex_pipe<2>(g);
+  else if (Te <= 3) launch_lex_pipe<3>(g);
+  else if (Te <= 4) launch_lex_pipe<4>(g);
+  else if (Te <= 6) launch_lex_pipe<6>(g);
+  else if (Te <= 8) launch_lex_pipe<8>(g);
+  else return false;
+  return true;
+}
+
 template <class K>
 static void launch_lex_kernel(Grid& g, K kernel, int LPR, const double* x_old, double* x_new) {
   int blocks_per_sm = 0;
   MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kBlock, 0));
   const int sms = sm_count_of(g.device);
   int blocks = blocks_per_sm * sms;
-  static int cap = -1;
-  if (cap < 0) { const char* e = getenv("MMG_LEX_BLOCKS"); cap = e ? atoi(e) : 0; }
-  if (cap > 0 && blocks > cap) blocks = cap;
+  const int cap = lex_block_cap(sms);            // fewer pollers: the sweep is latency bound, idle warps only load L2
+  if (blocks > cap) blocks = cap;
   const int need = grid_for(g.Lap.rows, LPR, 1 << 20);
   if (blocks > need) blocks = need;
   HybView A = g.Lap.view();
@@ -1006,6 +1147,11 @@ void op_sor(Grid& g, int smoother) {
   const HybMatrix& L = g.Lap;
   ensure_partials(g, (size_t)kRegBlocks + 2 * (sm_count_of(g.device) * 32 + 8));
   if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.have_colours) build_colouring(g);
+  if (smoother == MMG_SMOOTHER_LEXICOGRAPHIC && !g.neumann && g.Lap.n_ovf == 0 && g.props.iters >= 1 && g.Lap.W <= 257 && !env_int("MMG_LEX_NO_PIPE", 0)) {
+    TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 3);
+    sor_lex_pipelined(g);
+    return;
+  }
   for (int it = 0; it < g.props.iters; it++) {
     {
       const int launches = smoother == MMG_SMOOTHER_MULTICOLOUR ? g.n_colours + 1 : 2 + (L.reg_row >= 0 ? 2 : 0);
@@ -1019,7 +1165,7 @@ void op_sor(Grid& g, int smoother) {
 // ---- schedules (integer artefacts) ----------------------------------------------------------------
 void build_colouring(Grid& g) {
   // First-fit in ascending row order on the structurally symmetrised graph of the rows the sweep visits;
-  // the regularisation row takes the last colour (contract stated in oracle/mmg_oracle.cpp:build_colouring).
+  // the regularisation row takes the last colour (colouring contract: DESIGN.md §5).
   HostCsr A;
   hyb_to_csr(g.Lap, A, g.stream);
   const int R = A.rows;
