@@ -159,7 +159,7 @@ def workload_config(args, sides):
     return {
         "workload": "2D unit-square jittered cloud %dx%d = %d nodes, manufactured Dirichlet Poisson, %d-level V-cycle (sides %s), "
                     "fine polyDeg %d / coarse polyDeg 3, nu=5, omega=1.4" % (args.side, args.side, args.side ** 2, len(sides), sides, args.fine_poly),
-        "smoother": args.smoother, "l2": "inputs larger than L2 (finest operator alone is >1 GB vs 126 MB L2)",
+        "smoother": args.smoother + (" (omega=%g)" % args.mc_omega if args.smoother == "multicolour" else " (omega=1.4)"), "l2": "inputs larger than L2 (finest operator alone is >1 GB vs 126 MB L2)",
     }
 
 
@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--levels", type=int, default=None, help="number of levels (default: coarsen until the side is <= 16)")
     ap.add_argument("--fine-poly", type=int, default=4)
     ap.add_argument("--smoother", default="multicolour", choices=["multicolour", "lexicographic"])
+    ap.add_argument("--mc-omega", type=float, default=1.0, help="relaxation factor of the multicolour (throughput) mode")
     ap.add_argument("--cpu-side", type=int, default=500, help="finest lattice side of the bounded CPU sample")
     ap.add_argument("--cpu-cycles", type=int, default=3)
     ap.add_argument("--skip-cpu", action="store_true")
@@ -212,6 +213,8 @@ def main():
     fast = args.smoother == "multicolour"
     mg.set_smoother(capi.MULTICOLOUR if fast else capi.LEXICOGRAPHIC)
     mg.set_arithmetic(capi.ARITH_FAST if fast else capi.ARITH_REFERENCE_ORDER)
+    if fast:
+        mg.set_omega(args.mc_omega)     # multicolour ordering is unstable at the reference's omega=1.4
     fine = mg.grid(-1)
     A = fine.A_size
 
@@ -292,6 +295,7 @@ def main():
         if fast and not args.skip_lex:
             mg.set_smoother(capi.LEXICOGRAPHIC)
             mg.set_arithmetic(capi.ARITH_REFERENCE_ORDER)
+            mg.set_omega(1.4)
             fine.values_ = np.zeros(A)
             mg.vCycle(1)
             lex_ms = mg.time_vcycles(2) / 2

@@ -1,0 +1,223 @@
+// C++ facade: the reference's Grid / Multigrid / FractionalStepMultigrid classes re-created over the
+// C-ABI of libmmg (include/mmg.h), so the reference's drivers (testing_functions.cpp:328-350,
+// FractionalStepSim.cpp:114-200) keep their call sites.  Same method names, same argument meaning, same
+// mode strings ("fine"/"coarse", "dirichlet"/"neumann"); errors surface as std::runtime_error because
+// a CUDA failure has no CPU fallback to fall back to.
+//
+// The reference exposes raw public members (values_, source_, residuals_) that its drivers read and
+// write directly.  Here they are HostVector mirrors: reads pull from the device when the device copy is
+// newer, writes are pushed before the next device operation.  With real Eigen on the include path,
+// HostVector converts to and from Eigen::VectorXd.
+#pragma once
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "../../include/mmg.h"
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Dense>) && !defined(MMG_FACADE_NO_EIGEN)
+#include <Eigen/Dense>
+#define MMG_FACADE_HAVE_EIGEN 1
+#endif
+#endif
+
+namespace mmgf {
+
+typedef std::tuple<double, double, double> Point;   // grid.h:16
+
+inline void check(int rc, const char* what) {
+  if (rc != MMG_OK) throw std::runtime_error(std::string(what) + ": " + mmg_last_error());
+}
+
+// gridclasses.hpp:6-20
+struct GridProperties { int rbfExp = 3, polyDeg = 3, laplaceMatSize = 0, stencilSize = 25; double omega = 1.4; int iters = 5; };
+struct Boundary { int type = 0; std::vector<int> bcPoints; std::vector<double> values; };
+
+// host mirror of a device vector (values_ / source_)
+class HostVector {
+ public:
+  typedef int (*Getter)(mmg_grid*, double*);
+  typedef int (*Setter)(mmg_grid*, const double*);
+  HostVector() {}
+  void bind(mmg_grid* g, int n, Getter get, Setter set) { g_ = g; h_.assign(n, 0.0); get_ = get; set_ = set; device_newer_ = true; }
+  int rows() const { return (int)h_.size(); }
+  int size() const { return (int)h_.size(); }
+  double coeff(int i) const { pull(); return h_[i]; }
+  double operator()(int i) const { return coeff(i); }
+  double& coeffRef(int i) { pull(); host_newer_ = true; return h_[i]; }
+  double& operator()(int i) { return coeffRef(i); }
+  void setZero() { std::fill(h_.begin(), h_.end(), 0.0); device_newer_ = false; host_newer_ = true; }
+  const std::vector<double>& host() const { pull(); return h_; }
+  HostVector& operator=(const std::vector<double>& v) { h_ = v; device_newer_ = false; host_newer_ = true; return *this; }
+  double lpNorm1() const { pull(); double s = 0; for (double t : h_) s += t < 0 ? -t : t; return s; }
+#ifdef MMG_FACADE_HAVE_EIGEN
+  operator Eigen::VectorXd() const { pull(); return Eigen::Map<const Eigen::VectorXd>(h_.data(), (Eigen::Index)h_.size()); }
+  HostVector& operator=(const Eigen::VectorXd& v) { h_.assign(v.data(), v.data() + v.size()); device_newer_ = false; host_newer_ = true; return *this; }
+#endif
+  // facade internals
+  void push() { if (host_newer_) { check(set_(g_, h_.data()), "upload"); host_newer_ = false; } }
+  void invalidate() { device_newer_ = true; }
+ private:
+  void pull() const {
+    if (device_newer_ && !host_newer_) { check(get_(g_, const_cast<double*>(h_.data())), "download"); device_newer_ = false; }
+  }
+  mmg_grid* g_ = nullptr;
+  mutable std::vector<double> h_;
+  Getter get_ = nullptr;
+  Setter set_ = nullptr;
+  mutable bool device_newer_ = false;
+  bool host_newer_ = false;
+};
+
+class Multigrid;
+
+// grid.h:20-79
+class Grid {
+ public:
+  HostVector values_holder_;
+  HostVector* values_ = &values_holder_;   // the reference keeps a pointer (grid.h:23): (*grid->values_)(i) still compiles
+  HostVector source_;
+  std::vector<Point> points_;
+  std::vector<Boundary> boundaries_;
+  GridProperties properties_;
+  int laplaceMatSize_ = 0;
+  bool neumannFlag_ = false;
+  bool implicitFlag_ = false;
+
+  Grid(std::vector<Point> points, std::vector<Boundary> boundaries, GridProperties properties, const std::vector<double>& source, int device = 0)
+      : points_(std::move(points)), boundaries_(std::move(boundaries)), properties_(properties) {
+    const int n = (int)points_.size();
+    std::vector<double> x(n), y(n);
+    for (int i = 0; i < n; i++) { x[i] = std::get<0>(points_[i]); y[i] = std::get<1>(points_[i]); }
+    std::vector<int> type, ptr(1, 0), pts;
+    std::vector<double> vals;
+    for (const Boundary& b : boundaries_) {
+      type.push_back(b.type);
+      pts.insert(pts.end(), b.bcPoints.begin(), b.bcPoints.end());
+      std::vector<double> v = b.values;
+      v.resize(b.bcPoints.size(), 0.0);
+      vals.insert(vals.end(), v.begin(), v.end());
+      ptr.push_back((int)pts.size());
+      if (b.type == MMG_BC_NEUMANN) neumannFlag_ = true;
+    }
+    mmg_props p{properties.rbfExp, properties.polyDeg, properties.stencilSize, properties.iters, properties.omega};
+    check(mmg_grid_create(&h_, device, n, x.data(), y.data(), &p, source.data(), (int)source.size(), (int)boundaries_.size(), type.data(), ptr.data(),
+                          pts.data(), vals.data()), "Grid::Grid");
+    laplaceMatSize_ = n;
+    const int A = neumannFlag_ ? n + 1 : n;
+    values_holder_.bind(h_, A, mmg_grid_get_values, mmg_grid_set_values);
+    source_.bind(h_, A, mmg_grid_get_source, mmg_grid_set_source);
+  }
+  ~Grid() { if (h_ && owned_) mmg_grid_destroy(h_); }
+  Grid(const Grid&) = delete;
+  Grid& operator=(const Grid&) = delete;
+
+  void setBCFlag(int boundary, std::string type, std::vector<double> boundValue) {
+    const int t = type.compare("dirichlet") == 0 ? MMG_BC_DIRICHLET : MMG_BC_NEUMANN;   // grid.cpp:35
+    check(mmg_grid_set_implicit(h_, implicitFlag_), "implicitFlag_");
+    check(mmg_grid_set_bc_flag(h_, boundary, t, boundValue.data(), (int)boundValue.size()), "Grid::setBCFlag");
+    boundaries_.at(boundary).type = t;
+    boundaries_.at(boundary).values = boundValue;
+  }
+  void build_normal_vecs(const char* /*filename*/, std::string geomtype) {
+    if (geomtype != "square") throw std::runtime_error("build_normal_vecs: only the square geometry is built in; use mmg_grid_set_normal_vecs");
+    check(mmg_grid_build_normal_vecs_square(h_), "Grid::build_normal_vecs");
+  }
+  void rcm_order_points() { sync_flags(); push(); check(mmg_grid_rcm_order_points(h_), "Grid::rcm_order_points"); refresh(); }
+  void build_deriv_normal_bound() { sync_flags(); check(mmg_grid_build_deriv_normal_bound(h_), "Grid::build_deriv_normal_bound"); }
+  void build_laplacian() { sync_flags(); check(mmg_grid_build_laplacian(h_), "Grid::build_laplacian"); }
+  void modify_coeff_neumann(std::string coarse) { push(); check(mmg_grid_modify_coeff_neumann(h_, coarse == "coarse"), "Grid::modify_coeff_neumann"); source_.invalidate(); }
+  void push_inhomog_to_rhs() { sync_flags(); push(); check(mmg_grid_push_inhomog_to_rhs(h_), "Grid::push_inhomog_to_rhs"); source_.invalidate(); }
+  void boundaryOp(std::string coarse) { push(); check(mmg_grid_boundary_op(h_, coarse == "coarse"), "Grid::boundaryOp"); values_->invalidate(); }
+  void bound_eval_neumann() { push(); check(mmg_grid_bound_eval_neumann(h_), "Grid::bound_eval_neumann"); values_->invalidate(); }
+  // Grid::sor(laplaceMat_, values_, &source_): the reference always passes its own members (multigrid.cpp:79,93-94,108)
+  void sor() { push(); check(mmg_grid_sor(h_, MMG_SMOOTHER_LEXICOGRAPHIC), "Grid::sor"); values_->invalidate(); }
+  std::vector<double> residual() {
+    push();
+    std::vector<double> r(values_->rows());
+    check(mmg_grid_residual(h_, r.data()), "Grid::residual");
+    return r;
+  }
+  void fix_vector_bound_coarse(std::vector<double>* vec) { check(mmg_grid_fix_vector_bound_coarse(h_, vec->data()), "Grid::fix_vector_bound_coarse"); }
+  int getSize() const { return laplaceMatSize_; }
+  int getStencilSize() const { return properties_.stencilSize; }
+  int getPolyDeg() const { return properties_.polyDeg; }
+  mmg_grid* handle() { return h_; }
+
+ private:
+  friend class Multigrid;
+  void sync_flags() { check(mmg_grid_set_implicit(h_, implicitFlag_), "implicitFlag_"); }
+  void push() { values_->push(); source_.push(); }
+  void refresh() {   // after a reordering the host-side copies of points_/boundaries_ follow the device
+    const int n = laplaceMatSize_;
+    std::vector<double> x(n), y(n);
+    check(mmg_grid_get_points(h_, x.data(), y.data()), "points_");
+    for (int i = 0; i < n; i++) points_[i] = Point(x[i], y[i], 0.0);
+    for (size_t b = 0; b < boundaries_.size(); b++) {
+      int type = 0, count = 0;
+      check(mmg_grid_get_boundary(h_, (int)b, &type, &count, nullptr, nullptr), "boundaries_");
+      boundaries_[b].bcPoints.resize(count); boundaries_[b].values.resize(count);
+      check(mmg_grid_get_boundary(h_, (int)b, &type, &count, boundaries_[b].bcPoints.data(), boundaries_[b].values.data()), "boundaries_");
+    }
+    source_.invalidate();
+  }
+  mmg_grid* h_ = nullptr;
+  bool owned_ = true;
+};
+
+// multigrid.h:4-23; FractionalStepMultigrid (FracStepMultigrid.hpp:4-25) is the same class with the twin's flavour
+class Multigrid {
+ public:
+  std::vector<std::pair<int, Grid*>> grids_;
+  std::vector<double> residuals_;
+
+  explicit Multigrid(int flavour = MMG_FLAVOUR_MULTIGRID) { check(mmg_solver_create(&h_, flavour), "Multigrid::Multigrid"); }
+  ~Multigrid() {
+    for (auto& g : grids_) delete g.second;      // takes ownership like multigrid.cpp:10-16 (device grids go with the solver)
+    mmg_solver_destroy(h_);
+  }
+  void addGrid(Grid* grid) {
+    grid->push();
+    check(mmg_solver_add_grid(h_, grid->h_), "Multigrid::addGrid");
+    grid->owned_ = false;
+    grids_.push_back(std::pair<int, Grid*>(grid->getSize(), grid));
+    std::sort(grids_.begin(), grids_.end());     // multigrid.cpp:116-122
+  }
+  void buildMatrices() {
+    for (auto& g : grids_) g.second->push();
+    check(mmg_solver_build_matrices(h_), "Multigrid::buildMatrices");
+    for (auto& g : grids_) g.second->source_.invalidate();
+  }
+  void vCycle() {
+    for (auto& g : grids_) g.second->push();
+    check(mmg_solver_vcycle(h_, 1), "Multigrid::vCycle");
+    for (auto& g : grids_) { g.second->values_->invalidate(); g.second->source_.invalidate(); }
+    int n = 0;
+    check(mmg_solver_history_len(h_, &n), "residuals_");
+    residuals_.resize(n);
+    if (n) check(mmg_solver_get_history(h_, residuals_.data(), n), "residuals_");
+  }
+  double residual() {
+    for (auto& g : grids_) g.second->push();
+    double r = 0;
+    check(mmg_solver_residual(h_, &r), "Multigrid::residual");
+    return r;
+  }
+  void setSmoother(int smoother) { check(mmg_solver_set_smoother(h_, smoother), "setSmoother"); }
+  mmg_solver* handle() { return h_; }
+
+ private:
+  mmg_solver* h_ = nullptr;
+};
+
+class FractionalStepMultigrid : public Multigrid {
+ public:
+  FractionalStepMultigrid() : Multigrid(MMG_FLAVOUR_FRACSTEP) {}
+  void solveLoop() {}   // empty in the reference too (FracStepMultigrid.cpp:113-115)
+};
+
+}  // namespace mmgf
