@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--levels", type=int, default=None, help="number of levels (default: coarsen until the side is <= 16)")
     ap.add_argument("--fine-poly", type=int, default=4)
     ap.add_argument("--smoother", default="multicolour", choices=["multicolour", "lexicographic"])
-    ap.add_argument("--mc-omega", type=float, default=1.0, help="relaxation factor of the multicolour (throughput) mode")
+    ap.add_argument("--mc-omega", type=float, default=0.8, help="relaxation factor of the multicolour (throughput) mode")
     ap.add_argument("--cpu-side", type=int, default=500, help="finest lattice side of the bounded CPU sample")
     ap.add_argument("--cpu-cycles", type=int, default=3)
     ap.add_argument("--skip-cpu", action="store_true")

@@ -41,7 +41,7 @@ typedef struct mmg_props {
 enum { MMG_OK = 0, MMG_ERR_ARG = 1, MMG_ERR_CUDA = 2, MMG_ERR_STATE = 3, MMG_ERR_NCCL = 4, MMG_ERR_TIMEOUT = 5 };
 enum { MMG_BC_DIRICHLET = 1, MMG_BC_NEUMANN = 2 };                  /* Boundary::type, grid.cpp:35 */
 enum { MMG_FINE = 0, MMG_COARSE = 1 };                              /* the "fine"/"coarse" strings, grid.cpp:47,67 */
-enum { MMG_SMOOTHER_LEXICOGRAPHIC = 0, MMG_SMOOTHER_MULTICOLOUR = 1 };
+enum { MMG_SMOOTHER_LEXICOGRAPHIC = 0, MMG_SMOOTHER_MULTICOLOUR = 1, MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC = 2 };
 enum { MMG_FLAVOUR_MULTIGRID = 0, MMG_FLAVOUR_FRACSTEP = 1 };
 /* row sums folded in the reference's ascending-column order (bit-faithful, default) or with reordered warp reductions (throughput) */
 enum { MMG_ARITH_REFERENCE_ORDER = 0, MMG_ARITH_FAST = 1 };
@@ -111,6 +111,8 @@ int mmg_grid_set_laplacian_csr(mmg_grid* g, int rows, const int* ptr, const int*
                                const int* nb_ptr, const int* nb_idx, const double* nb_val);
 /* integer artefacts of the GPU schedules (bit-exact against the oracle) */
 int mmg_grid_get_colouring(mmg_grid* g, int* n_colours, int* colour);              /* per row, -1 for rows the sweep skips */
+int mmg_grid_set_block_size(mmg_grid* g, int rows_per_block);                      /* block-lexicographic smoother: rows per block (default 4096) */
+int mmg_grid_get_block_colouring(mmg_grid* g, int* n_blocks, int* n_colours, int* colour, int cap); /* colour of each block (bit-exact vs oracle) */
 int mmg_grid_get_lex_levels(mmg_grid* g, int* n_levels, int* level);               /* dependency-DAG level of each row, -1 if skipped */
 
 /* ---------------------------------------------------------------- Multigrid ----------------- */
@@ -130,6 +132,7 @@ int mmg_solver_set_smoother(mmg_solver* s, int smoother);                       
 int mmg_solver_restrict(mmg_solver* s, int level);                                 /* source_{i-1} = R_i * residual_i + masks, multigrid.cpp:81-86 */
 int mmg_solver_prolong_correct(mmg_solver* s, int level);                          /* values_i += P_{i-1} * values_{i-1}, multigrid.cpp:102-106 */
 int mmg_solver_coarse_solve(mmg_solver* s);                                        /* coarsest level: zero guess + 2 sor calls, multigrid.cpp:92-95 */
+int mmg_solver_set_block_size(mmg_solver* s, int rows_per_block);                  /* block-lexicographic smoother, every grid */
 int mmg_solver_set_omega(mmg_solver* s, double omega);                             /* properties_.omega of every grid (gridclasses.hpp:12) */
 int mmg_solver_set_arithmetic(mmg_solver* s, int arithmetic);                      /* MMG_ARITH_* for every grid of the solver */
 int mmg_solver_vcycle(mmg_solver* s, int n_cycles);                                /* Multigrid::vCycle multigrid.cpp:62-110, n times, no host sync inside */

@@ -11,7 +11,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--fmad=false",   # reference arithmetic is uncontracted
     "-ccbin", "/usr/bin/g++",
-]
+] + (["-DMMG_FAST_ROWS=" + os.environ["MMG_FAST_ROWS"]] if os.environ.get("MMG_FAST_ROWS") else [])
 
 
 def _stale():

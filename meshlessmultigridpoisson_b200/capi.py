@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libmmg.so")
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_TIMEOUT = range(6)
 BC_DIRICHLET, BC_NEUMANN = 1, 2
 FINE, COARSE = 0, 1
-LEXICOGRAPHIC, MULTICOLOUR = 0, 1
+LEXICOGRAPHIC, MULTICOLOUR, BLOCK_LEXICOGRAPHIC = 0, 1, 2
 FLAVOUR_MULTIGRID, FLAVOUR_FRACSTEP = 0, 1
 ARITH_REFERENCE_ORDER, ARITH_FAST = 0, 1
 MAT_LAPLACE, MAT_NEUMANN_COEFFS, MAT_RESTRICT, MAT_PROLONG, MAT_DERIVX, MAT_DERIVY, MAT_UVLAPLACE = range(7)
@@ -81,6 +81,8 @@ SIGNATURES = {
     "mmg_grid_set_laplacian_csr": [_vp, _i, _ip, _ip, _dp, _vp, _vp, _vp, _vp],
     "mmg_grid_get_colouring": [_vp, C.POINTER(_i), _ip],
     "mmg_grid_get_lex_levels": [_vp, C.POINTER(_i), _ip],
+    "mmg_grid_set_block_size": [_vp, _i],
+    "mmg_grid_get_block_colouring": [_vp, C.POINTER(_i), C.POINTER(_i), _vp, _i],
     "mmg_solver_create": [C.POINTER(_vp), _i],
     "mmg_solver_destroy": [_vp],
     "mmg_solver_add_grid": [_vp, _vp],
@@ -95,6 +97,7 @@ SIGNATURES = {
     "mmg_solver_restrict": [_vp, _i],
     "mmg_solver_prolong_correct": [_vp, _i],
     "mmg_solver_coarse_solve": [_vp],
+    "mmg_solver_set_block_size": [_vp, _i],
     "mmg_solver_set_omega": [_vp, _d],
     "mmg_solver_set_arithmetic": [_vp, _i],
     "mmg_solver_vcycle": [_vp, _i],
@@ -363,6 +366,16 @@ class Grid:
         _ck(self.L, self.L.mmg_grid_get_colouring(self.h, n, c))
         return n.value, c
 
+    def set_block_size(self, rows_per_block):
+        _ck(self.L, self.L.mmg_grid_set_block_size(self.h, rows_per_block))
+
+    def block_colouring(self):
+        nb, nc = _i(), _i()
+        _ck(self.L, self.L.mmg_grid_get_block_colouring(self.h, nb, nc, None, 0))
+        c = np.empty(nb.value, np.int32)
+        _ck(self.L, self.L.mmg_grid_get_block_colouring(self.h, nb, nc, _opt(c), c.size))
+        return nc.value, c
+
     def lex_levels(self):
         n, c = _i(), np.empty(self.A_size, np.int32)
         _ck(self.L, self.L.mmg_grid_get_lex_levels(self.h, n, c))
@@ -421,6 +434,9 @@ class Multigrid:
 
     def set_smoother(self, smoother):
         _ck(self.L, self.L.mmg_solver_set_smoother(self.h, smoother))
+
+    def set_block_size(self, rows_per_block):
+        _ck(self.L, self.L.mmg_solver_set_block_size(self.h, rows_per_block))
 
     def set_omega(self, omega):
         _ck(self.L, self.L.mmg_solver_set_omega(self.h, omega))

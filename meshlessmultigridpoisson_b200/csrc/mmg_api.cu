@@ -118,6 +118,7 @@ static void set_laplacian_csr(Grid& g, int rows, const int* ptr, const int* idx,
   }
   g.have_laplacian = true;
   g.have_colours = false;
+  g.have_blocks = false;
 }
 
 // Grid::push_inhomog_to_rhs grid.cpp:664-685 — O(|boundary| * stencil) entries; done through a host round trip of
@@ -521,6 +522,25 @@ int mmg_grid_get_colouring(mmg_grid* g, int* n_colours, int* colour) {
   std::memcpy(colour, gr.colour_host.data(), sizeof(int) * gr.A);
   API_END
 }
+int mmg_grid_set_block_size(mmg_grid* g, int rows_per_block) {
+  API_BEGIN
+  NEED(g);
+  MMG_REQUIRE(rows_per_block >= 32, MMG_ERR_ARG, "block size must be at least 32 rows");
+  if (G(g).block_size != rows_per_block) { G(g).block_size = rows_per_block; G(g).have_blocks = false; }
+  API_END
+}
+int mmg_grid_get_block_colouring(mmg_grid* g, int* n_blocks, int* n_colours, int* colour, int cap) {
+  API_BEGIN
+  NEED(g); NEED(n_blocks); NEED(n_colours);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  MMG_REQUIRE(gr.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+  if (!gr.have_blocks) build_block_colouring(gr);
+  *n_blocks = (int)gr.blk_colour.size();
+  *n_colours = gr.n_blk_colours;
+  if (colour) for (int i = 0; i < *n_blocks && i < cap; i++) colour[i] = gr.blk_colour[i];
+  API_END
+}
 int mmg_grid_get_lex_levels(mmg_grid* g, int* n_levels, int* level) {
   API_BEGIN
   NEED(g); NEED(n_levels); NEED(level);
@@ -666,7 +686,8 @@ int mmg_solver_get_interp_csr(mmg_solver* s, int which, int level, int* ptr, int
 int mmg_solver_set_smoother(mmg_solver* s, int smoother) {
   API_BEGIN
   NEED(s);
-  MMG_REQUIRE(smoother == MMG_SMOOTHER_LEXICOGRAPHIC || smoother == MMG_SMOOTHER_MULTICOLOUR, MMG_ERR_ARG, "unknown smoother");
+  MMG_REQUIRE(smoother == MMG_SMOOTHER_LEXICOGRAPHIC || smoother == MMG_SMOOTHER_MULTICOLOUR || smoother == MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC, MMG_ERR_ARG,
+              "unknown smoother");
   S(s).smoother = smoother;
   API_END
 }
@@ -704,6 +725,14 @@ int mmg_solver_coarse_solve(mmg_solver* s) {
   op_sor(c, so.smoother);
   MMG_CUDA(cudaStreamSynchronize(so.stream));
   solver_check_abort(so);
+  API_END
+}
+int mmg_solver_set_block_size(mmg_solver* s, int rows_per_block) {
+  API_BEGIN
+  NEED(s);
+  MMG_REQUIRE(rows_per_block >= 32, MMG_ERR_ARG, "block size must be at least 32 rows");
+  for (Grid* g : S(s).grids)
+    if (g->block_size != rows_per_block) { g->block_size = rows_per_block; g->have_blocks = false; }
   API_END
 }
 int mmg_solver_set_omega(mmg_solver* s, double omega) {
@@ -841,6 +870,12 @@ int mmg_solver_reset_timers(mmg_solver* s) {
   timers_collect(so.timers);
   for (int lv = 0; lv < kMaxLevels; lv++)
     for (int i = 0; i < MMG_T_COUNT; i++) { so.timers.ms[lv][i] = 0; so.timers.launches[lv][i] = 0; so.timers.bytes[lv][i] = 0; }
+  API_END
+}
+// diagnostics, not part of include/mmg.h: clock64 stamps of one CTA of the chunked lexicographic kernel (MMG_LEX_TRACE=1)
+int mmg_debug_lex_trace(long long* out, int n) {
+  API_BEGIN
+  mmg::debug_lex_trace(out, n);
   API_END
 }
 int mmg_solver_launch_count(mmg_solver* s, int64_t* launches) {

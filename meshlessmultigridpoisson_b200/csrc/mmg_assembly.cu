@@ -740,7 +740,7 @@ void asm_build_laplacian(Grid& g) {
     g.diags.assign(g.A, 0.0);
     ddiag.download(g.diags.data(), N, g.stream);
     g.nbc = HostCsr();
-    g.have_laplacian = true; g.have_colours = false;
+    g.have_laplacian = true; g.have_colours = false; g.have_blocks = false;
     return;
   }
   // Neumann / mixed grid: weights from the device, triplet bookkeeping of grid.cpp:553-661 on the host
@@ -802,7 +802,7 @@ void asm_build_laplacian(Grid& g) {
     csr_from_triplets(A, g.A, g.A, trip);
   }
   hyb_from_csr(g.Lap, A, true, true, g.stream);
-  g.have_laplacian = true; g.have_colours = false;
+  g.have_laplacian = true; g.have_colours = false; g.have_blocks = false;
 }
 
 }  // namespace mmg

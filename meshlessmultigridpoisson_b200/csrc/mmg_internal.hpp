@@ -175,6 +175,12 @@ struct Grid {
   std::vector<int> colour_ptr;           // n_colours+1
   DevBuf<int> colour_rows;               // rows grouped by colour, ascending inside a colour
   std::vector<int> colour_host;          // per-row colour (-1 skipped)
+  // block-lexicographic schedule
+  int block_size = 4096;
+  bool have_blocks = false;
+  int n_blk_colours = 0;
+  std::vector<int> blk_colour, blk_phase_ptr;
+  DevBuf<int> blk_phase_blocks;          // block ids grouped by colour
   // per-level assembly state (device kNN lists etc.) lives in assembly.cu
   void* asm_state = nullptr;
 
@@ -211,6 +217,7 @@ void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fin
 void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P);
 void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class);
 void build_colouring(Grid& g);
+void build_block_colouring(Grid& g);
 void compute_lex_levels(Grid& g, std::vector<int>& level, int& n_levels);
 
 // ---- assembly (assembly.cu) ---------------------------------------------------------------------
@@ -230,5 +237,6 @@ struct TimedScope {
   ~TimedScope();
 };
 void timers_collect(Timers& t);
+void debug_lex_trace(long long* out, int n);
 
 }  // namespace mmg

@@ -13,6 +13,10 @@
 
 #include "mmg_internal.hpp"
 
+#ifndef MMG_FAST_ROWS
+#define MMG_FAST_ROWS 4
+#endif
+
 namespace mmg {
 
 namespace {
@@ -379,6 +383,7 @@ __global__ void __launch_bounds__(kBlock) k_bound_eval(HybView A, const int* __r
 // `dcol` handling: when a diagonal product is pending (diag-first storage) it is inserted just
 // before the first entry whose column exceeds `row`, i.e. at its ascending-column position.
 __device__ __forceinline__ double fold_in_order(double s, double p, int col, int cnt, bool subtract, bool& diag_pending, double pdiag, int row) {
+  __syncwarp();
 #pragma unroll
   for (int l = 0; l < 32; l++) {
     if (l < cnt) {
@@ -484,6 +489,8 @@ __global__ void __launch_bounds__(32) k_regdot_exact(const int* __restrict__ col
 // s <- s - p_l for lanes l = 0..cnt-1 in lane order.  Lanes >= cnt hold 0.0 (x - 0.0 == x bit for bit), so whole
 // groups of 8 are folded without per-element predicates: the shuffles hoist, the DSUB chain is the only dependency.
 __device__ __forceinline__ double fold_sub32(double s, double p, int cnt) {
+  __syncwarp();   // reconverge: after the lane-dependent polling loops the warp is formally diverged, and every __shfl_sync then takes
+                  // the compiler's BRA.DIV slow path (~25 cycles per shuffle instead of ~2; measured in profiles/r01_lex_trace.txt)
 #pragma unroll
   for (int g8 = 0; g8 < 4; g8++) {
     if (cnt > g8 * 8) {
@@ -655,6 +662,162 @@ __global__ void __launch_bounds__(kBlock) k_sor_lex_pipe(HybView A, const unsign
   }
 }
 
+// Chunked variant of the pipelined sweep.  The critical path of the lexicographic DAG runs mostly along
+// CONSECUTIVE rows (scripts/dag_chunks.py: with 16-row chunks ~78 % of its edges stay inside a chunk), and a
+// hand-off through L2 costs ~1.2 us while one through shared memory costs ~0.3 us.  So a CTA of K warps takes a
+// chunk of K consecutive rows (warp w <-> row lo+w): dependencies on rows of the same chunk are polled in shared
+// memory, everything else (earlier chunks of this sweep, the previous sweep) in L2 as before.  CTAs are dealt to
+// sweeps round-robin and walk their chunks in increasing order, so the deadlock-freedom argument of
+// k_sor_lex_pipe carries over unchanged.  Reference-order arithmetic.
+// optional timing trace of one CTA (diagnostics; MMG_LEX_TRACE=1 and mmg_debug_lex_trace())
+__device__ long long g_lex_trace[16 * 64];
+__device__ int g_lex_trace_on = 0;
+#define LEX_STAMP(slot) do { if (tracing && lane == 0) g_lex_trace[(warp * 8 + (slot)) % (16 * 64)] = clock64(); } while (0)
+
+template <int T, int K>
+__global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b, double* xs,
+                                                          size_t stride, int iters, double omega, int* abort_flag, long long timeout_cycles) {
+  __shared__ double xs_s[K];                 // this chunk's new values
+  __shared__ unsigned long long bars[K];     // bars[w]: one arrival per in-chunk dependency of row lo+w
+  __shared__ unsigned depmask[K];            // bit j of depmask[w]: row lo+w reads row lo+j (j < w)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sweep = 1 + blockIdx.x % iters;
+  const int q = blockIdx.x / iters, Q = gridDim.x / iters;
+  if (q >= Q) return;
+  const double* x_old = xs + (size_t)(sweep - 1) * stride;
+  double* x_new = xs + (size_t)sweep * stride;
+  volatile double* xs_v = xs_s;
+  const unsigned bar_me = (unsigned)__cvta_generic_to_shared(&bars[warp]);
+  const unsigned bar_lane = (unsigned)__cvta_generic_to_shared(&bars[lane < K ? lane : 0]);
+  const long long t_start = clock64();
+  const int nchunks = (A.rows + K - 1) / K;
+  // bars[w] collects exactly K arrivals per chunk (one from every warp of the CTA): warps that row lo+w does not read
+  // arrive at once, the rows it reads arrive when their value is in xs_s.  Initialised once; the phase parity flips per chunk.
+  if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_me), "r"(K) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  unsigned parity = 0;
+  for (int chunk = q; chunk < nchunks; chunk += Q, parity ^= 1u) {
+    const int lo = chunk * K;
+    const int row = lo + warp;
+    const bool live = row < A.rows && rowflag[row] == 0;
+    const bool tracing = g_lex_trace_on && blockIdx.x == 2 * iters && chunk == q + 20 * Q && warp < 16;
+    __syncthreads();                                   // the previous chunk's slots are no longer in use, its barrier phases are complete
+    LEX_STAMP(0);
+    double prod[T];
+    double pv[T];
+    const double* pp[T];
+    int ps[T];
+    unsigned pend_g = 0, in_chunk = 0, mydeps = 0;
+    int m = 0;
+    double wd = 0.0, bi = 0.0;
+    if (live) {
+      const int len = A.len[row];
+      const double* __restrict__ v = row_val(A, row);
+      const int* __restrict__ c = row_col(A, row);
+      m = len < A.W ? len : A.W;
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        const int k = 1 + lane + t * 32;
+        prod[t] = 0.0; pv[t] = 0.0; pp[t] = nullptr; ps[t] = 0;
+        if (k < m) {
+          pv[t] = v[k];
+          const int col = c[k];
+          if (col >= lo && col < row && rowflag[col] == 0) { ps[t] = col - lo; in_chunk |= 1u << t; mydeps |= 1u << (col - lo); }
+          else { pp[t] = (col > row ? x_old : x_new) + col; pend_g |= 1u << t; }
+        }
+      }
+      wd = omega / v[0];
+      bi = b[row];
+    }
+    const unsigned deps = __reduce_or_sync(0xffffffffu, mydeps);
+    if (lane == 0) depmask[warp] = deps;
+    __syncthreads();
+    const bool notify = live && lane < K && lane > warp && ((depmask[lane] >> warp) & 1u);   // rows of this chunk that read mine
+    if (lane < K && !notify) {                                                                // everyone else gets my arrival now
+      unsigned long long state;
+      asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar_lane) : "memory");
+    }
+    if (!live) continue;
+    double xo = 0.0;
+    bool need_xo = lane == 0;
+    unsigned spins = 0;
+    bool aborted = false;
+    LEX_STAMP(1);
+    {
+      // Watch phase.  Rows complete roughly in index order, so the LAST dependency to resolve is almost always the largest
+      // column below the chunk (this sweep) or the largest column above the row (previous sweep).  Only those two words are
+      // polled (lanes 0 and 1) until they turn valid: one sector per round instead of one per pending entry, which keeps
+      // the SM's load/shuffle pipe free for the warps that are folding (the per-entry polls saturated it: profiles/r01_lex_trace.txt).
+      int cnew = -1, cold = -1;
+#pragma unroll
+      for (int t = 0; t < T; t++)
+        if (pend_g & (1u << t)) {
+          const int col = (int)(pp[t] - (pp[t] >= x_new ? x_new : x_old));
+          if (pp[t] >= x_new) cnew = max(cnew, col); else cold = max(cold, col);
+        }
+      cnew = __reduce_max_sync(0xffffffffu, cnew);
+      cold = __reduce_max_sync(0xffffffffu, cold);
+      const double* watch = lane == 0 ? (cnew >= 0 ? x_new + cnew : nullptr) : lane == 1 ? (cold >= 0 ? x_old + cold : nullptr) : nullptr;
+      bool waiting = watch != nullptr;
+      while (__any_sync(0xffffffffu, waiting)) {
+        if (waiting) waiting = is_sentinel(ld_relaxed(watch));
+        if ((++spins & 0xff) == 0) {
+          if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
+        }
+      }
+    }
+    LEX_STAMP(2);
+    while (!aborted && __any_sync(0xffffffffu, pend_g != 0 || need_xo)) {      // dependencies outside the chunk: L2 polls
+      double xv[T];
+#pragma unroll
+      for (int t = 0; t < T; t++) xv[t] = (pend_g & (1u << t)) ? ld_relaxed(pp[t]) : 0.0;
+      if (need_xo) { xo = ld_relaxed(x_old + row); need_xo = is_sentinel(xo); }
+#pragma unroll
+      for (int t = 0; t < T; t++)
+        if ((pend_g & (1u << t)) && !is_sentinel(xv[t])) { prod[t] = __dmul_rn(pv[t], xv[t]); pend_g &= ~(1u << t); }
+      if ((++spins & 0xff) == 0) {
+        if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
+      }
+    }
+    LEX_STAMP(3);
+    if (deps && !aborted) {                                        // dependencies inside the chunk: hardware-suspended wait
+      unsigned done = 0;
+      spins = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint, so the wait really sleeps
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_me), "r"(parity), "r"(0x989680u) : "memory");
+        if (!done && (++spins & 0x3f) == 0) {
+          if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < T; t++)
+        if (in_chunk & (1u << t)) prod[t] = __dmul_rn(pv[t], xs_v[ps[t]]);
+    }
+    LEX_STAMP(4);
+    double xi = 0.0;
+    if (!aborted) {
+      double s = 0.0;
+#pragma unroll
+      for (int t = 0; t < T; t++) s = fold_sub32(s, prod[t], m - 1 - t * 32);
+      xi = __dadd_rn(s, bi);
+      xi = __dmul_rn(xi, wd);
+      xi = __dadd_rn(xi, __dmul_rn(1 - omega, __shfl_sync(0xffffffffu, xo, 0)));
+    }
+    LEX_STAMP(5);
+    if (lane == 0) { xs_v[warp] = xi; st_relaxed(x_new + row, xi); }   // (on abort: a finite value, so nobody behind us hangs)
+    __syncwarp();
+    if (notify) {
+      unsigned long long state;
+      asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar_lane) : "memory");
+    }
+    LEX_STAMP(6);
+  }
+}
+
 // xs[0] = x; xs[s>=1][i] = skipped(i) ? x[i] : sentinel
 __global__ void __launch_bounds__(kBlock) k_pipe_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x, double* xs, size_t stride,
                                                       int iters, int total) {
@@ -664,6 +827,126 @@ __global__ void __launch_bounds__(kBlock) k_pipe_init(const unsigned char* __res
   const bool skipped = rowflag[i] != 0;
   xs[i] = xi;
   for (int s = 1; s <= iters; s++) xs[(size_t)s * stride + i] = skipped ? xi : __longlong_as_double((long long)kSentinelBits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-lexicographic SOR (throughput mode that keeps the lexicographic character).
+// Rows are cut into contiguous blocks of B rows; same-colour blocks do not touch each other, so one
+// launch sweeps every block of a colour concurrently.  Inside a block the sweep is the reference's
+// ascending-row Gauss-Seidel: row i waits (sentinel in x_work) only for rows j<i of ITS OWN block and
+// reads every other column from x, which no block of this colour modifies.  The DAG depth is that of
+// one block (independent of N) instead of the whole grid.  Positions are dealt block-interleaved
+// (p -> block p % nblk, offset p / nblk) so all blocks advance together; dependencies have smaller p.
+// Reference-order arithmetic: bit-identical to the oracle's sor_blocklex.
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(kBlock) k_sor_blk(HybView A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b,
+                                                    const double* x, double* x_work, const int* __restrict__ phase_blocks, int nblk, int B,
+                                                    double omega, int* abort_flag, long long timeout_cycles) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long t_start = clock64();
+  const long long total = (long long)nblk * B;
+  for (long long p = warp; p < total; p += nwarps) {
+    const int blk = phase_blocks[(int)(p % nblk)];
+    const int lo = blk * B;
+    const int row = lo + (int)(p / nblk);
+    if (row >= A.rows || rowflag[row] != 0) continue;
+    const int len = A.len[row];
+    const double* __restrict__ v = row_val(A, row);
+    const int* __restrict__ c = row_col(A, row);
+    const int m = len < A.W ? len : A.W;
+    double prod[T];
+    double pv[T];
+    int pc[T];
+    unsigned pend = 0;
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      const int k = 1 + lane + t * 32;
+      prod[t] = 0.0; pv[t] = 0.0; pc[t] = 0;
+      if (k < m) {
+        const double a = v[k];
+        const int col = c[k];
+        if (col < row && col >= lo) { pv[t] = a; pc[t] = col; pend |= 1u << t; }
+        else prod[t] = __dmul_rn(a, x[col]);
+      }
+    }
+    const double wd = omega / v[0];
+    const double bi = b[row];
+    const double xo_term = __dmul_rn(1 - omega, x[row]);
+    unsigned spins = 0;
+    bool aborted = false;
+    while (__any_sync(0xffffffffu, pend != 0)) {
+      double xv[T];
+#pragma unroll
+      for (int t = 0; t < T; t++) xv[t] = (pend & (1u << t)) ? ld_relaxed(x_work + pc[t]) : 0.0;
+#pragma unroll
+      for (int t = 0; t < T; t++)
+        if ((pend & (1u << t)) && !is_sentinel(xv[t])) { prod[t] = __dmul_rn(pv[t], xv[t]); pend &= ~(1u << t); }
+      if ((++spins & 0xff) == 0) {
+        if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
+      }
+    }
+    if (aborted) { if (lane == 0) st_relaxed(x_work + row, 0.0); return; }
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < T; t++) s = fold_sub32(s, prod[t], m - 1 - t * 32);
+    if (lane == 0) {
+      double xi = __dadd_rn(s, bi);
+      xi = __dmul_rn(xi, wd);
+      xi = __dadd_rn(xi, xo_term);
+      st_relaxed(x_work + row, xi);
+    }
+  }
+}
+
+// before a colour phase: x_work <- sentinel on the rows the phase will write (old value on rows it skips)
+__global__ void __launch_bounds__(kBlock) k_blk_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x, double* x_work,
+                                                     const int* __restrict__ phase_blocks, int nblk, int B, int rows) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)nblk * B) return;
+  const int row = phase_blocks[(int)(p / B)] * B + (int)(p % B);
+  if (row < rows) x_work[row] = rowflag[row] != 0 ? x[row] : __longlong_as_double((long long)kSentinelBits);
+}
+// after a colour phase: publish the block results
+__global__ void __launch_bounds__(kBlock) k_blk_merge(const unsigned char* __restrict__ rowflag, double* x, const double* __restrict__ x_work,
+                                                      const int* __restrict__ phase_blocks, int nblk, int B, int rows) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)nblk * B) return;
+  const int row = phase_blocks[(int)(p / B)] * B + (int)(p % B);
+  if (row < rows && rowflag[row] == 0) x[row] = x_work[row];
+}
+// block adjacency bitmap: bit (a, b) set when a swept row of block a stores a swept column of block b != a
+__global__ void __launch_bounds__(kBlock) k_blk_adjacency(HybView A, const unsigned char* __restrict__ rowflag, int B, int nb, unsigned* bitmap) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int words = (nb + 31) / 32;
+  for (int row = warp; row < A.rows; row += nwarps) {
+    if (rowflag[row] != 0) continue;
+    const int len = A.len[row];
+    const int* __restrict__ c = row_col(A, row);
+    const int m = len < A.W ? len : A.W;
+    const int a = row / B;
+    for (int k = lane; k < m; k += 32) {
+      const int col = c[k];
+      if (col < A.rows && rowflag[col] == 0) {
+        const int bb = col / B;
+        if (bb != a) atomicOr(bitmap + (size_t)a * words + (bb >> 5), 1u << (bb & 31));
+      }
+    }
+    if (len > A.W) {
+      const int o = ovf_find(A, row);
+      for (int k = A.ovf_ptr[o] + lane; k < A.ovf_ptr[o + 1]; k += 32) {
+        const int col = A.ovf_col[k];
+        if (col < A.rows && rowflag[col] == 0) {
+          const int bb = col / B;
+          if (bb != a) atomicOr(bitmap + (size_t)a * words + (bb >> 5), 1u << (bb & 31));
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) k_sor_mc_exact(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
@@ -694,6 +977,193 @@ __global__ void __launch_bounds__(kBlock) k_bound_eval_exact(HybView A, const in
     double diag = 0.0;
     const double t = row_dot_in_order(A, row, x, true, true, true, b[row], &diag);
     if (lane == 0) x[row] = t / diag;
+  }
+}
+
+// ================================================================================================
+// Throughput ("fast") kernels, second generation.  The first-generation loops above were latency bound
+// (ncu: long-scoreboard stalls, ~25-30 % of HBM peak, profiles/r01_*): one row per lane group and a
+// load -> gather -> FMA chain per iteration.  Here the per-lane trip count is a compile-time constant,
+// two rows are in flight per lane group, all matrix loads are issued before any gather and all gathers
+// before any arithmetic, the matrix stream is marked evict-first in L2 and the gathered vector
+// evict-last so the 8*N-byte x stays L2 resident under the 12*nnz-byte stream.
+// ================================================================================================
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ldg_keep(const double* p, unsigned long long pol) {   // gathered vector: keep in L2
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double ldg_stream_f64(const double* p, unsigned long long pol) {   // matrix stream: read once
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ldg_stream_s32(const int* p, unsigned long long pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+template <int LPR, int ITER>
+struct RowRegs {
+  double v[ITER];
+  int c[ITER];
+};
+template <int LPR, int ITER>
+__device__ __forceinline__ void row_fetch(const HybView& A, int row, bool valid, int gl, unsigned long long pol, RowRegs<LPR, ITER>& r, int& len) {
+  len = valid ? A.len[row] : 0;
+  const double* __restrict__ v = row_val(A, valid ? row : 0);
+  const int* __restrict__ c = row_col(A, valid ? row : 0);
+  const int m = len < A.W ? len : A.W;
+#pragma unroll
+  for (int t = 0; t < ITER; t++) {
+    const int k = gl + t * LPR;
+    const bool ok = k < m;
+    r.v[t] = ok ? ldg_stream_f64(v + k, pol) : 0.0;
+    r.c[t] = ok ? ldg_stream_s32(c + k, pol) : -1;
+  }
+}
+// acc = (+/-) sum_k v_k * x[c_k]; when skip_first the slot-0 entry (the diagonal) is returned in diag instead
+template <int LPR, int ITER, bool SUB, bool DIAG0>
+__device__ __forceinline__ double row_accumulate(const RowRegs<LPR, ITER>& r, const double* x, unsigned long long pol, int gl, double& diag) {
+  double xx[ITER];
+#pragma unroll
+  for (int t = 0; t < ITER; t++) xx[t] = r.c[t] >= 0 ? ldg_keep(x + r.c[t], pol) : 0.0;
+  double acc = 0.0;
+#pragma unroll
+  for (int t = 0; t < ITER; t++) {
+    if (DIAG0 && t == 0 && gl == 0) { diag = r.v[0]; continue; }
+    const double p = __dmul_rn(r.v[t], xx[t]);
+    acc = SUB ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
+  }
+  return acc;
+}
+template <int LPR, bool SUB>
+__device__ __forceinline__ double row_overflow(const HybView& A, int row, int len, const double* x, int gl, double acc) {
+  if (len > A.W) {
+    const int o = ovf_find(A, row);
+    for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) {
+      const double p = __dmul_rn(A.ovf_val[k], x[A.ovf_col[k]]);
+      acc = SUB ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
+    }
+  }
+  return acc;
+}
+
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, const double* __restrict__ b, double* y,
+                                                  const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
+                                                  double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
+  double num = 0.0, den = 0.0;
+  for (int row0 = warp * GPW * ROWS; row0 < A.rows; row0 += nwarps * GPW * ROWS) {
+    RowRegs<LPR, ITER> r[ROWS];
+    int row[ROWS], len[ROWS];
+    bool valid[ROWS];
+    double acc[ROWS];
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      row[h] = row0 + h * GPW + lane / LPR;
+      valid[h] = row[h] < A.rows;
+      row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
+    }
+    double dummy;
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) acc[h] = row_accumulate<LPR, ITER, false, false>(r[h], x, keep, gl, dummy);
+    if (A.n_ovf) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) if (valid[h]) acc[h] = row_overflow<LPR, false>(A, row[h], len[h], x, gl, acc[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      if (valid[h] && gl == 0) {
+        const int flag = rowflag ? rowflag[row[h]] : 0;
+        if (op == OP_SPMV) {
+          y[row[h]] = acc[h];
+        } else if (op == OP_RESID) {
+          const double bi = b[row[h]];
+          double t = __dsub_rn(bi, acc[h]);
+          if (flag == 1) t = 0.0;
+          if (y) y[row[h]] = t;
+          num += fabs(t);
+          den += fabs(bi);
+        } else if (op == OP_PROLONG) {
+          if (!(mask_dirichlet && flag == 1)) y[row[h]] = __dadd_rn(y[row[h]], acc[h]);
+        } else {
+          double t = acc[h];
+          if (flag == 1) t = 0.0;
+          if (mask_neumann && flag == 2) t = 0.0;
+          y[row[h]] = t;
+        }
+      }
+    }
+  }
+  if (partial) {
+    block_sum2(num, den);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = num; partial[2 * blockIdx.x + 1] = den; }
+  }
+}
+
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
+                                                    double omega) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
+  for (int i0 = warp * GPW * ROWS; i0 < count; i0 += nwarps * GPW * ROWS) {
+    RowRegs<LPR, ITER> r[ROWS];
+    int row[ROWS], len[ROWS];
+    bool valid[ROWS];
+    double acc[ROWS], diag[ROWS];
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      const int i = i0 + h * GPW + lane / LPR;
+      valid[h] = i < count;
+      row[h] = valid[h] ? rows_list[i] : 0;
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate<LPR, ITER, true, true>(r[h], x, keep, gl, diag[h]); }
+    if (A.n_ovf) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) if (valid[h]) acc[h] = row_overflow<LPR, true>(A, row[h], len[h], x, gl, acc[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+    if (gl == 0) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) {
+        if (valid[h]) {
+          double xi = __dadd_rn(acc[h], b[row[h]]);
+          xi = __dmul_rn(xi, omega / diag[h]);
+          xi = __dadd_rn(xi, __dmul_rn(1 - omega, x[row[h]]));
+          x[row[h]] = xi;
+        }
+      }
+    }
   }
 }
 
@@ -737,6 +1207,22 @@ void dispatch_lpr(int W, F&& f) {
   else f(std::integral_constant<int, 8>());
 }
 
+// (lanes per row, entries per lane) for the second-generation fast kernels; false if the width is outside the table
+template <class F>
+bool dispatch_lpr_iter(int W, F&& f) {
+  const int lpr = lanes_for_width(W);
+  const int iter = (W + lpr - 1) / lpr;
+#define MMG_CASE(L_, I_) if (lpr == L_ && iter == I_) { f(std::integral_constant<int, L_>(), std::integral_constant<int, I_>()); return true; }
+  MMG_CASE(32, 2) MMG_CASE(32, 3) MMG_CASE(32, 4)
+  MMG_CASE(16, 2) MMG_CASE(16, 3)
+  MMG_CASE(8, 1) MMG_CASE(8, 2) MMG_CASE(8, 3)
+#undef MMG_CASE
+  return false;
+}
+constexpr int kSpmvRows = MMG_FAST_ROWS;   // rows in flight per lane group: 4 is best for the streaming SpMV kernels (profiles/r01_kernel_rates.txt)
+constexpr int kMcRows = 2;                 // ... and 2 for the multicolour sweep, whose gathers do not coalesce
+int grid_for2(int rows, int lpr, int sm_count, int per = kSpmvRows) { return grid_for((rows + per - 1) / per, lpr, sm_count); }
+
 void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
                  double* partial, int* nblocks_out, int device, cudaStream_t s, bool exact) {
   const int sms = sm_count_of(device);
@@ -747,12 +1233,19 @@ void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y
     MMG_CUDA(cudaGetLastError());
     return;
   }
-  dispatch_lpr(M.W, [&](auto L) {
-    constexpr int LPR = decltype(L)::value;
-    const int blocks = grid_for(M.rows, LPR, sms);
+  const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(M.W, [&](auto L, auto I) {
+    constexpr int LPR = decltype(L)::value, ITER = decltype(I)::value;
+    const int blocks = grid_for2(M.rows, LPR, sms);
     if (nblocks_out) *nblocks_out = blocks;
-    k_spmv<LPR><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial);
+    k_spmv2<LPR, ITER, kSpmvRows><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial);
   });
+  if (!done)
+    dispatch_lpr(M.W, [&](auto L) {
+      constexpr int LPR = decltype(L)::value;
+      const int blocks = grid_for(M.rows, LPR, sms);
+      if (nblocks_out) *nblocks_out = blocks;
+      k_spmv<LPR><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial);
+    });
   MMG_CUDA(cudaGetLastError());
 }
 
@@ -1019,6 +1512,30 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 static int lex_block_cap(int sms) { static int v = -2; if (v == -2) v = env_int("MMG_LEX_BLOCKS", 0); return v > 0 ? v : 2 * sms; }
 static unsigned lex_sleep_ns() { static int v = -2; if (v == -2) v = env_int("MMG_LEX_SLEEP_NS", 0); return (unsigned)v; }
 
+template <int T, int K>
+static void launch_lex_chunk(Grid& g, size_t stride) {
+  const int iters = g.props.iters;
+  { const int on = env_int("MMG_LEX_TRACE", 0); MMG_CUDA(cudaMemcpyToSymbolAsync(g_lex_trace_on, &on, sizeof(int), 0, cudaMemcpyHostToDevice, g.stream)); }
+  int blocks_per_sm = 0;
+  MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_lex_chunk<T, K>, K * 32, 0));
+  const int sms = sm_count_of(g.device);
+  int blocks = std::min(blocks_per_sm * sms, env_int("MMG_LEX_CHUNK_BLOCKS", 1 << 20));
+  const int need = ((g.Lap.rows + K - 1) / K) * iters;
+  if (blocks > need) blocks = need;
+  if (blocks < iters) blocks = iters;
+  HybView A = g.Lap.view();
+  const unsigned char* rf = g.rowflag.p;
+  const double* b = g.b.p;
+  double* xs = g.xs.p;
+  size_t st = stride;
+  int it = iters;
+  double omega = g.props.omega;
+  int* abortp = g.abort_flag.p;
+  long long timeout = 6000000000ll;
+  void* args[] = {&A, &rf, &b, &xs, &st, &it, &omega, &abortp, &timeout};
+  MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_lex_chunk<T, K>, dim3(blocks), dim3(K * 32), args, 0, g.stream));
+}
+
 template <int T>
 static void launch_lex_pipe(Grid& g) {
   const int iters = g.props.iters;
@@ -1026,6 +1543,14 @@ static void launch_lex_pipe(Grid& g) {
   if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
   k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
   MMG_CUDA(cudaGetLastError());
+  const int chunk = env_int("MMG_LEX_CHUNK", 0);   // chunked variant (shared-memory hand-offs): opt-in, see DESIGN.md §5
+  if (chunk > 0) {
+    if (chunk == 8) launch_lex_chunk<T, 8>(g, stride);
+    else if (chunk == 32) launch_lex_chunk<T, 32>(g, stride);
+    else launch_lex_chunk<T, 16>(g, stride);
+    MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
+    return;
+  }
   int blocks_per_sm = 0;
   MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_lex_pipe<T>, kBlock, 0));
   const int sms = sm_count_of(g.device);
@@ -1113,6 +1638,88 @@ static void sor_lex_sweep(Grid& g) {
   std::swap(g.x.p, g.x_alt.p);
 }
 
+// block colouring: adjacency bitmap on the device, first-fit in ascending block order on the host (nb is small)
+void build_block_colouring(Grid& g) {
+  const HybMatrix& L = g.Lap;
+  const int B = g.block_size, R = L.rows;
+  MMG_REQUIRE(B >= 32, MMG_ERR_ARG, "block size must be at least 32 rows");
+  const int nb = (R + B - 1) / B, words = (nb + 31) / 32;
+  DevBuf<unsigned> bitmap;
+  bitmap.alloc((size_t)nb * words);
+  bitmap.zero(g.stream);
+  k_blk_adjacency<<<grid_for(R, 32, sm_count_of(g.device)), kBlock, 0, g.stream>>>(L.view(), g.rowflag.p, B, nb, bitmap.p);
+  MMG_CUDA(cudaGetLastError());
+  std::vector<unsigned> bm = bitmap.to_host(g.stream);
+  auto adjacent = [&](int a, int b) { return ((bm[(size_t)a * words + (b >> 5)] >> (b & 31)) & 1u) || ((bm[(size_t)b * words + (a >> 5)] >> (a & 31)) & 1u); };
+  g.blk_colour.assign(nb, -1);
+  int ncol = 0;
+  std::vector<int> mark;
+  for (int a = 0; a < nb; a++) {
+    for (int b = 0; b < a; b++)
+      if (adjacent(a, b)) {
+        if ((int)mark.size() <= g.blk_colour[b]) mark.resize(g.blk_colour[b] + 1, -1);
+        mark[g.blk_colour[b]] = a;
+      }
+    int c = 0;
+    while (c < (int)mark.size() && mark[c] == a) c++;
+    g.blk_colour[a] = c;
+    ncol = std::max(ncol, c + 1);
+  }
+  g.n_blk_colours = ncol;
+  g.blk_phase_ptr.assign(ncol + 1, 0);
+  for (int a = 0; a < nb; a++) g.blk_phase_ptr[g.blk_colour[a] + 1]++;
+  for (int c = 0; c < ncol; c++) g.blk_phase_ptr[c + 1] += g.blk_phase_ptr[c];
+  std::vector<int> order(nb), pos(g.blk_phase_ptr.begin(), g.blk_phase_ptr.end() - 1);
+  for (int a = 0; a < nb; a++) order[pos[g.blk_colour[a]]++] = a;
+  g.blk_phase_blocks.upload(order, g.stream);
+  g.sync();
+  g.have_blocks = true;
+}
+
+template <int T>
+static void launch_blk(Grid& g, const int* phase_blocks, int nblk) {
+  int blocks_per_sm = 0;
+  MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_blk<T>, kBlock, 0));
+  const int sms = sm_count_of(g.device);
+  int blocks = std::min(blocks_per_sm * sms, env_int("MMG_BLK_BLOCKS", 6 * sms));
+  const long long need = ((long long)nblk * g.block_size * 32 + kBlock - 1) / kBlock;
+  if (blocks > need) blocks = (int)need;
+  HybView A = g.Lap.view();
+  const unsigned char* rf = g.rowflag.p;
+  const double* b = g.b.p;
+  const double* x = g.x.p;
+  double* xw = g.x_alt.p;
+  int B = g.block_size;
+  double omega = g.props.omega;
+  int* abortp = g.abort_flag.p;
+  long long timeout = 6000000000ll;
+  void* args[] = {&A, &rf, &b, &x, &xw, &phase_blocks, &nblk, &B, &omega, &abortp, &timeout};
+  MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_blk<T>, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+}
+
+static void sor_blk_sweep(Grid& g) {
+  const HybMatrix& L = g.Lap;
+  const int B = g.block_size;
+  const int Te = (L.W - 1 + 31) / 32;
+  for (int c = 0; c < g.n_blk_colours; c++) {
+    const int first = g.blk_phase_ptr[c], nblk = g.blk_phase_ptr[c + 1] - first;
+    if (nblk == 0) continue;
+    const int* pb = g.blk_phase_blocks.p + first;
+    const long long total = (long long)nblk * B;
+    const int nb = (int)((total + kBlock - 1) / kBlock);
+    k_blk_init<<<nb, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.x_alt.p, pb, nblk, B, L.rows);
+    if (Te <= 1) launch_blk<1>(g, pb, nblk);
+    else if (Te <= 2) launch_blk<2>(g, pb, nblk);
+    else if (Te <= 3) launch_blk<3>(g, pb, nblk);
+    else if (Te <= 4) launch_blk<4>(g, pb, nblk);
+    else if (Te <= 6) launch_blk<6>(g, pb, nblk);
+    else if (Te <= 8) launch_blk<8>(g, pb, nblk);
+    else throw Error(MMG_ERR_ARG, "stencil width outside the block-lexicographic kernel's dispatch table");
+    k_blk_merge<<<nb, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.x_alt.p, pb, nblk, B, L.rows);
+    MMG_CUDA(cudaGetLastError());
+  }
+}
+
 static void sor_mc_sweep(Grid& g) {
   const HybMatrix& L = g.Lap;
   const int sms = sm_count_of(g.device);
@@ -1124,14 +1731,23 @@ static void sor_mc_sweep(Grid& g) {
       k_sor_mc_exact<<<grid_for(count, 32, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
     }
   } else {
-    dispatch_lpr(L.W, [&](auto Lc) {
-      constexpr int LPR = decltype(Lc)::value;
+    const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+      constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
       for (int c = 0; c < ncol_rows; c++) {
         const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
         if (count == 0) continue;
-        k_sor_mc<LPR><<<grid_for(count, LPR, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
+        k_sor_mc2<LPR, ITER, kMcRows><<<grid_for2(count, LPR, sms, kMcRows), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
       }
     });
+    if (!done)
+      dispatch_lpr(L.W, [&](auto Lc) {
+        constexpr int LPR = decltype(Lc)::value;
+        for (int c = 0; c < ncol_rows; c++) {
+          const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
+          if (count == 0) continue;
+          k_sor_mc<LPR><<<grid_for(count, LPR, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
+        }
+      });
   }
   MMG_CUDA(cudaGetLastError());
   if (L.reg_row >= 0) {
@@ -1152,14 +1768,25 @@ void op_sor(Grid& g, int smoother) {
     sor_lex_pipelined(g);
     return;
   }
+  if (smoother == MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC) {
+    MMG_REQUIRE(!g.neumann, MMG_ERR_STATE, "the block-lexicographic smoother is implemented for grids without Neumann boundaries");
+    if (!g.have_blocks) build_block_colouring(g);
+  }
   for (int it = 0; it < g.props.iters; it++) {
     {
-      const int launches = smoother == MMG_SMOOTHER_MULTICOLOUR ? g.n_colours + 1 : 2 + (L.reg_row >= 0 ? 2 : 0);
+      const int launches = smoother == MMG_SMOOTHER_MULTICOLOUR ? g.n_colours + 1 : smoother == MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC ? 3 * g.n_blk_colours : 2 + (L.reg_row >= 0 ? 2 : 0);
       TimedScope ts(g, MMG_T_SOR, L.matrix_bytes() + (int64_t)g.A * 28, launches);
-      if (smoother == MMG_SMOOTHER_MULTICOLOUR) sor_mc_sweep(g); else sor_lex_sweep(g);
+      if (smoother == MMG_SMOOTHER_MULTICOLOUR) sor_mc_sweep(g);
+      else if (smoother == MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC) sor_blk_sweep(g);
+      else sor_lex_sweep(g);
     }
     op_bound_eval_neumann(g);  // grid.cpp:144
   }
+}
+
+void debug_lex_trace(long long* out, int n) {
+  MMG_CUDA(cudaDeviceSynchronize());
+  MMG_CUDA(cudaMemcpyFromSymbol(out, g_lex_trace, sizeof(long long) * std::min(n, 16 * 64)));
 }
 
 // ---- schedules (integer artefacts) ----------------------------------------------------------------

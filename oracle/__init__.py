@@ -45,6 +45,9 @@ def lib():
         "orc_mg_build": (i, [v]),
         "orc_mg_nlevels": (i, [v]),
         "orc_mg_set_multicolour": (None, [v, i]),
+        "orc_mg_set_smoother": (None, [v, i, i]),
+        "orc_lv_sor_blocklex": (None, [v, i, i]),
+        "orc_lv_block_colouring": (i, [v, i, i, _ip, i]),
         "orc_mg_vcycle": (i, [v, i]),
         "orc_mg_time_vcycles": (d, [v, i]),
         "orc_mg_solve": (i, [v, d, i, C.POINTER(d)]),
@@ -197,6 +200,15 @@ class Level:
     def sor_multicolour(self):
         self.L.orc_lv_sor_multicolour(self.h, self.l)
 
+    def sor_blocklex(self, block_size):
+        self.L.orc_lv_sor_blocklex(self.h, self.l, block_size)
+
+    def block_colouring(self, block_size):
+        nb = (self.n + block_size - 1) // block_size
+        c = np.empty(nb, np.int32)
+        n = self.L.orc_lv_block_colouring(self.h, self.l, block_size, c, nb)
+        return n, c
+
     def residual(self):
         r = np.empty(self.A)
         self.L.orc_lv_residual(self.h, self.l, r)
@@ -304,6 +316,10 @@ class Multigrid:
 
     def set_multicolour(self, on):
         self.L.orc_mg_set_multicolour(self.h, int(on))
+
+    def set_smoother(self, smoother, block_size=4096):
+        """0 lexicographic (the reference), 1 multicolour, 2 block-lexicographic"""
+        self.L.orc_mg_set_smoother(self.h, smoother, block_size)
 
     def vcycle(self, n=1):
         if self.L.orc_mg_vcycle(self.h, n):

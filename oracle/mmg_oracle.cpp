@@ -713,6 +713,65 @@ void Grid::sor_multicolour(const Csr& A, std::vector<double>& values, const std:
   }
 }
 
+void Grid::build_block_colouring() {
+  const Csr& A = laplaceMat_;
+  const int R = neumannFlag_ ? A.rows - 1 : A.rows;          // the regularisation row is not part of any block
+  const int B = block_size_;
+  const int nb = (R + B - 1) / B;
+  auto swept = [&](int i) { return i < R && bcFlags_[i] == 0; };
+  std::vector<std::vector<int>> adj(nb);
+  for (int i = 0; i < R; i++) {
+    if (!swept(i)) continue;
+    for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++) {
+      const int j = A.idx[k];
+      if (j == i || !swept(j)) continue;
+      const int a = i / B, b = j / B;
+      if (a != b) { adj[a].push_back(b); adj[b].push_back(a); }
+    }
+  }
+  block_colour_.assign(nb, -1);
+  n_block_colours_ = 0;
+  std::vector<int> mark;
+  for (int a = 0; a < nb; a++) {
+    for (int b : adj[a])
+      if (b < a) {
+        if ((int)mark.size() <= block_colour_[b]) mark.resize(block_colour_[b] + 1, -1);
+        mark[block_colour_[b]] = a;
+      }
+    int c = 0;
+    while (c < (int)mark.size() && mark[c] == a) c++;
+    block_colour_[a] = c;
+    n_block_colours_ = std::max(n_block_colours_, c + 1);
+  }
+}
+
+void Grid::sor_blocklex(const Csr& A, std::vector<double>& values, const std::vector<double>& rhs) {
+  if (block_colour_.empty()) build_block_colouring();
+  const int R = neumannFlag_ ? A.rows - 1 : A.rows;
+  const int B = block_size_, nb = (int)block_colour_.size();
+  auto update = [&](int i) {   // same row update as Grid::sor (grid.cpp:122-141)
+    double x_i = 0, diagCoeff = 0;
+    for (int j = A.ptr[i]; j < A.ptr[i + 1]; j++) {
+      if (A.idx[j] == i) { diagCoeff = A.val[j]; continue; }
+      x_i -= A.val[j] * values[A.idx[j]];
+    }
+    x_i += rhs[i];
+    x_i *= properties_.omega / diagCoeff;
+    x_i += (1 - properties_.omega) * values[i];
+    values[i] = x_i;
+  };
+  for (int it = 0; it < properties_.iters; it++) {
+    for (int c = 0; c < n_block_colours_; c++)
+      for (int b = 0; b < nb; b++) {
+        if (block_colour_[b] != c) continue;
+        for (int i = b * B; i < std::min(R, (b + 1) * B); i++)
+          if (bcFlags_[i] == 0) update(i);
+      }
+    if (neumannFlag_) update(A.rows - 1);   // regularisation row last, as in the lexicographic sweep
+    bound_eval_neumann();
+  }
+}
+
 std::vector<int> Grid::lex_levels() const {
   // level(i) = 1 + max level over stored columns j<i that the sweep also visits; skipped rows -1.
   const Csr& A = laplaceMat_;
@@ -845,7 +904,8 @@ void Multigrid::buildMatrices() {  // multigrid.cpp:34-60
 }
 
 void Multigrid::smooth(Grid* g) {
-  if (multicolour) g->sor_multicolour(g->laplaceMat_, g->values_, g->source_);
+  if (blocklex) g->sor_blocklex(g->laplaceMat_, g->values_, g->source_);
+  else if (multicolour) g->sor_multicolour(g->laplaceMat_, g->values_, g->source_);
   else g->sor(g->laplaceMat_, g->values_, g->source_);
 }
 

@@ -116,6 +116,15 @@ struct Grid {
   void sor_multicolour(const Csr& A, std::vector<double>& values, const std::vector<double>& rhs);
   // dependency-DAG level sets of one lexicographic sweep (integer artefact)
   std::vector<int> lex_levels() const;
+  // ---- oracle restatement of the block-lexicographic smoother (NOT in the reference) -----
+  // rows are cut into contiguous blocks of block_size_ rows; blocks are coloured first-fit in ascending block
+  // order on the symmetrised block graph; a sweep visits colours in order and, inside a block, rows in ascending
+  // order with the reference's row update.  Same-colour blocks are independent, so the GPU runs them concurrently.
+  int block_size_ = 4096;
+  std::vector<int> block_colour_;
+  int n_block_colours_ = 0;
+  void build_block_colouring();
+  void sor_blocklex(const Csr& A, std::vector<double>& values, const std::vector<double>& rhs);
 
  private:
   void build_cells();
@@ -145,6 +154,7 @@ struct FractionalStepGrid : Grid {
 struct Multigrid {
   bool fracstep = false;                 // FracStepMultigrid.cpp:23 (interp polyDeg) and :64-67 (1-grid shortcut)
   bool multicolour = false;              // oracle restatement of the multicolour mode
+  bool blocklex = false;                 // oracle restatement of the block-lexicographic mode
   std::vector<std::pair<int, Grid*>> grids_;
   std::vector<Csr> restrictionMatrices_; // [i] : N_{i-1} x N_i, i>=1
   std::vector<Csr> prolongMatrices_;     // [i] : N_{i+1} x N_i, i<L-1

@@ -93,6 +93,26 @@ int orc_mg_build(void* h) {
 }
 int orc_mg_nlevels(void* h) { return (int)static_cast<Handle*>(h)->mg.grids_.size(); }
 void orc_mg_set_multicolour(void* h, int on) { static_cast<Handle*>(h)->mg.multicolour = on != 0; }
+// smoother: 0 lexicographic (reference), 1 multicolour, 2 block-lexicographic with the given block size
+void orc_mg_set_smoother(void* h, int smoother, int block_size) {
+  Multigrid& mg = static_cast<Handle*>(h)->mg;
+  mg.multicolour = smoother == 1;
+  mg.blocklex = smoother == 2;
+  if (smoother == 2)
+    for (auto& g : mg.grids_) { g.second->block_size_ = block_size; g.second->block_colour_.clear(); }
+}
+void orc_lv_sor_blocklex(void* h, int l, int block_size) {
+  Grid* g = lv(h, l);
+  if (g->block_size_ != block_size) { g->block_size_ = block_size; g->block_colour_.clear(); }
+  g->sor_blocklex(g->laplaceMat_, g->values_, g->source_);
+}
+int orc_lv_block_colouring(void* h, int l, int block_size, int* colour, int cap) {
+  Grid* g = lv(h, l);
+  g->block_size_ = block_size;
+  g->build_block_colouring();
+  for (int i = 0; i < (int)g->block_colour_.size() && i < cap; i++) colour[i] = g->block_colour_[i];
+  return g->n_block_colours_;
+}
 int orc_mg_vcycle(void* h, int n) {
   ORC_TRY
   for (int i = 0; i < n; i++) static_cast<Handle*>(h)->mg.vCycle();

@@ -26,3 +26,12 @@ g.sor(capi.LEXICOGRAPHIC)
 t0 = time.perf_counter(); g.sor(capi.LEXICOGRAPHIC); dt = time.perf_counter() - t0
 hops = n + (iters - 1) * (half + 1) if not os.environ.get("MMG_LEX_NO_PIPE") else n * iters
 print("rows %d half-band %d iters %d env %s: %.2f ms, %.0f ns per hop" % (n, half, iters, {k: v for k, v in os.environ.items() if k.startswith("MMG_")}, dt * 1e3, dt / hops * 1e9))
+if os.environ.get("MMG_LEX_TRACE"):
+    import ctypes
+    buf = (ctypes.c_longlong * 128)()
+    g.L.mmg_debug_lex_trace(buf, 128)
+    t = np.array(buf[:128]).reshape(16, 8)
+    base = t[:, 0].min()
+    print("warp: start loaded round1 smem-only deps-done folded stored | rounds   (cycles since the chunk barrier)")
+    for w in range(16):
+        print("%2d: %s | %d" % (w, " ".join("%7d" % (v - base) for v in t[w, :7]), t[w, 7]))

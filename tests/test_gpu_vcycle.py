@@ -110,3 +110,39 @@ def test_fast_arithmetic_history(libmmg, multicolour):
     mg, s = run_pair([13, 25, 50, 100], oracle.KIND_DIRICHLET, 4, 25, multicolour, fast=True)
     check_history_fast(mg, s)
     assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
+
+
+# ---------------------------------------------------------------- block-lexicographic smoother (throughput mode)
+@pytest.mark.parametrize("block", [64, 256, 4096])
+def test_block_lexicographic_sor_is_bit_identical_to_the_oracle(libmmg, block):
+    mg = oracle.make_hierarchy([13, 25, 50], kind=oracle.KIND_DIRICHLET, fine_poly=4)
+    s = H.gpu_solver_from_oracle(mg)
+    s.set_block_size(block)
+    for l in range(mg.nlevels):
+        lv, g = mg.level(l), s.grid(l)
+        nc, col = lv.block_colouring(block)
+        nc2, col2 = g.block_colouring()
+        assert nc == nc2 and np.array_equal(col, col2)                     # integer artefact: bit-exact
+        v = 1e-3 * H.random_values(lv, 51 + l)
+        lv.set_vec(oracle.VEC_VALUES, v); g.values_ = v
+        lv.sor_blocklex(block); g.sor(capi.BLOCK_LEXICOGRAPHIC)
+        assert np.array_equal(g.values_, lv.values), (l, H.rel_err(g.values_, lv.values))
+
+
+@pytest.mark.parametrize("block", [256, 4096])
+def test_block_lexicographic_vcycle_history(libmmg, block):
+    mg = oracle.make_hierarchy([13, 25, 50, 100], kind=oracle.KIND_DIRICHLET, fine_poly=4)
+    s = H.gpu_solver_from_oracle(mg)
+    mg.set_smoother(2, block)
+    s.set_smoother(capi.BLOCK_LEXICOGRAPHIC); s.set_block_size(block)
+    mg.vcycle(20); s.vCycle(20)
+    check_history(mg, s)
+    assert H.rel_l2(s.grid(-1).values_, mg.level(-1).values) < TOL_SOLUTION
+
+
+def test_block_lexicographic_with_one_block_is_the_reference_sweep(libmmg):
+    mg = oracle.make_hierarchy([13, 25, 50], kind=oracle.KIND_DIRICHLET, fine_poly=4)
+    a, b = H.gpu_solver_from_oracle(mg), H.gpu_solver_from_oracle(mg)
+    b.set_smoother(capi.BLOCK_LEXICOGRAPHIC); b.set_block_size(1 << 20)
+    a.vCycle(8); b.vCycle(8)
+    assert np.array_equal(a.residuals_, b.residuals_)
