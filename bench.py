@@ -246,9 +246,18 @@ def main():
     sor = tm_fine["sor"]
     achieved = sor["bytes"] / (sor["ms"] * 1e-3) / 1e9 if sor["ms"] > 0 else 0.0
     shares = {k: round(v["ms"] / max(1e-9, sum(x["ms"] for x in tm_all.values())), 4) for k, v in tm_all.items()}
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "k_sor_mc (finest level, one launch per colour)" if fast else "k_sor_lex_exact (finest level)",
-                "peak_source": peak_src, "bytes_per_launch_set": sor["bytes"] // max(1, sor["launches"]),
+    traffic, per_launch = None, None
+    if fast:
+        from meshlessmultigridpoisson_b200.problems import stencil_size
+        counts = fine.colour_counts()
+        per_launch = int(counts.max()) * (12 * stencil_size(args.fine_poly) + 28)     # largest colour phase = one launch
+        if args.side == 2000 and args.fine_poly == 4:
+            # dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full (profiles/r01_sor_mc2_4M_ncu.txt)
+            traffic = 208287488 + 5096448
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_sor_mc2 (finest level, one launch per colour; achieved = bytes of all colour launches / their CUDA-event time)"
+                if fast else "k_sor_lex_pipe (finest level)",
+                "peak_source": peak_src, "algorithmic_bytes_largest_launch": per_launch, "bytes_per_sweep": sor["bytes"] // max(1, 2 * 5 * args.steps),
                 "sor_share_of_step": shares.get("sor"), "class_shares": shares,
                 "whole_cycle_GBps": algorithmic_bytes_per_cycle(sides, args.fine_poly) / (ms_per_step * 1e-3) / 1e9}
 

@@ -111,6 +111,7 @@ int mmg_grid_set_laplacian_csr(mmg_grid* g, int rows, const int* ptr, const int*
                                const int* nb_ptr, const int* nb_idx, const double* nb_val);
 /* integer artefacts of the GPU schedules (bit-exact against the oracle) */
 int mmg_grid_get_colouring(mmg_grid* g, int* n_colours, int* colour);              /* per row, -1 for rows the sweep skips */
+int mmg_grid_get_colour_counts(mmg_grid* g, int* n_colours, int* counts, int cap);  /* rows per colour class (one multicolour launch each) */
 int mmg_grid_set_block_size(mmg_grid* g, int rows_per_block);                      /* block-lexicographic smoother: rows per block (default 4096) */
 int mmg_grid_get_block_colouring(mmg_grid* g, int* n_blocks, int* n_colours, int* colour, int cap); /* colour of each block (bit-exact vs oracle) */
 int mmg_grid_get_lex_levels(mmg_grid* g, int* n_levels, int* level);               /* dependency-DAG level of each row, -1 if skipped */

@@ -81,6 +81,7 @@ SIGNATURES = {
     "mmg_grid_set_laplacian_csr": [_vp, _i, _ip, _ip, _dp, _vp, _vp, _vp, _vp],
     "mmg_grid_get_colouring": [_vp, C.POINTER(_i), _ip],
     "mmg_grid_get_lex_levels": [_vp, C.POINTER(_i), _ip],
+    "mmg_grid_get_colour_counts": [_vp, C.POINTER(_i), _vp, _i],
     "mmg_grid_set_block_size": [_vp, _i],
     "mmg_grid_get_block_colouring": [_vp, C.POINTER(_i), C.POINTER(_i), _vp, _i],
     "mmg_solver_create": [C.POINTER(_vp), _i],
@@ -365,6 +366,13 @@ class Grid:
         n, c = _i(), np.empty(self.A_size, np.int32)
         _ck(self.L, self.L.mmg_grid_get_colouring(self.h, n, c))
         return n.value, c
+
+    def colour_counts(self):
+        n = _i()
+        _ck(self.L, self.L.mmg_grid_get_colour_counts(self.h, n, None, 0))
+        c = np.empty(n.value, np.int32)
+        _ck(self.L, self.L.mmg_grid_get_colour_counts(self.h, n, _opt(c), c.size))
+        return c
 
     def set_block_size(self, rows_per_block):
         _ck(self.L, self.L.mmg_grid_set_block_size(self.h, rows_per_block))

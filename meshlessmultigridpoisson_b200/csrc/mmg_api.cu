@@ -522,6 +522,17 @@ int mmg_grid_get_colouring(mmg_grid* g, int* n_colours, int* colour) {
   std::memcpy(colour, gr.colour_host.data(), sizeof(int) * gr.A);
   API_END
 }
+int mmg_grid_get_colour_counts(mmg_grid* g, int* n_colours, int* counts, int cap) {
+  API_BEGIN
+  NEED(g); NEED(n_colours);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  MMG_REQUIRE(gr.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
+  if (!gr.have_colours) build_colouring(gr);
+  *n_colours = gr.n_colours;
+  if (counts) for (int c = 0; c < gr.n_colours && c < cap; c++) counts[c] = gr.colour_ptr[c + 1] - gr.colour_ptr[c];
+  API_END
+}
 int mmg_grid_set_block_size(mmg_grid* g, int rows_per_block) {
   API_BEGIN
   NEED(g);

@@ -174,6 +174,7 @@ struct Grid {
   int n_colours = 0;
   std::vector<int> colour_ptr;           // n_colours+1
   DevBuf<int> colour_rows;               // rows grouped by colour, ascending inside a colour
+  DevBuf<int> colour_ptr_dev;            // colour_ptr on the device (persistent multicolour kernel)
   std::vector<int> colour_host;          // per-row colour (-1 skipped)
   // block-lexicographic schedule
   int block_size = 4096;

@@ -1014,6 +1014,13 @@ __device__ __forceinline__ int ldg_stream_s32(const int* p, unsigned long long p
   return v;
 }
 
+// pull the chunk of a row that this lane group will process on its NEXT trip into L2 (one 128-byte line per lane)
+template <int LPR>
+__device__ __forceinline__ void prefetch_chunk_l2(const HybView& A, int row, int gl) {
+  const unsigned char* p = A.chunks + (size_t)row * A.chunk_bytes + (size_t)gl * 128;
+  if ((size_t)gl * 128 < A.chunk_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int LPR, int ITER>
 struct RowRegs {
   double v[ITER];
@@ -1063,7 +1070,7 @@ __device__ __forceinline__ double row_overflow(const HybView& A, int row, int le
 template <int LPR, int ITER, int ROWS>
 __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, const double* __restrict__ b, double* y,
                                                   const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
-                                                  double* __restrict__ partial) {
+                                                  double* __restrict__ partial, int prefetch) {
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const unsigned gmask = group_mask<LPR>(lane);
@@ -1082,6 +1089,10 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, co
       row[h] = row0 + h * GPW + lane / LPR;
       valid[h] = row[h] < A.rows;
       row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
+    }
+    if (prefetch) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) { const int nr = row[h] + nwarps * GPW * ROWS; if (nr < A.rows) prefetch_chunk_l2<LPR>(A, nr, gl); }
     }
     double dummy;
 #pragma unroll
@@ -1123,8 +1134,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, co
 }
 
 template <int LPR, int ITER, int ROWS>
-__global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
-                                                    double omega) {
+__device__ __forceinline__ void mc_phase(const HybView& A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
+                                         double omega, int prefetch) {
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const unsigned gmask = group_mask<LPR>(lane);
@@ -1145,6 +1156,13 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __rest
     }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
+    if (prefetch) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) {
+        const int ni = i0 + nwarps * GPW * ROWS + h * GPW + lane / LPR;
+        if (ni < count) prefetch_chunk_l2<LPR>(A, rows_list[ni], gl);
+      }
+    }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate<LPR, ITER, true, true>(r[h], x, keep, gl, diag[h]); }
     if (A.n_ovf) {
@@ -1165,6 +1183,28 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __rest
       }
     }
   }
+}
+
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
+                                                    double omega, int prefetch) {
+  mc_phase<LPR, ITER, ROWS>(A, rows_list, count, b, x, omega, prefetch);
+}
+
+// All colours of all `iters` sweeps of a grid without Neumann rows in ONE cooperative launch, a grid-wide barrier
+// between colour phases.  On the coarse levels a colour phase is a few microseconds of work, so per-colour launches
+// were launch-gap bound (ncu launch list, profiles/r01_launches_mc_4M_summary.txt: the W=25 levels took 44 % of the
+// cycle in 2100 launches).
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kBlock) k_sor_mc_all(HybView A, const int* __restrict__ rows_list, const int* __restrict__ colour_ptr, int ncolours,
+                                                       int iters, const double* __restrict__ b, double* x, double omega) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  for (int it = 0; it < iters; it++)
+    for (int c = 0; c < ncolours; c++) {
+      const int first = colour_ptr[c], count = colour_ptr[c + 1] - first;
+      mc_phase<LPR, ITER, ROWS>(A, rows_list + first, count, b, x, omega, 0);
+      grid.sync();
+    }
 }
 
 __global__ void k_scatter(const int* __restrict__ idx, const double* __restrict__ vals, int count, double* dst, int use_zero) {
@@ -1219,6 +1259,8 @@ bool dispatch_lpr_iter(int W, F&& f) {
 #undef MMG_CASE
   return false;
 }
+// MMG_FAST_PREFETCH=n: persistent grid of n CTAs per SM with next-trip L2 prefetch (0 = one trip per warp, no prefetch)
+int fast_prefetch() { static int v = -2; if (v == -2) { const char* e = getenv("MMG_FAST_PREFETCH"); v = e ? atoi(e) : 0; } return v; }
 constexpr int kSpmvRows = MMG_FAST_ROWS;   // rows in flight per lane group: 4 is best for the streaming SpMV kernels (profiles/r01_kernel_rates.txt)
 constexpr int kMcRows = 2;                 // ... and 2 for the multicolour sweep, whose gathers do not coalesce
 int grid_for2(int rows, int lpr, int sm_count, int per = kSpmvRows) { return grid_for((rows + per - 1) / per, lpr, sm_count); }
@@ -1235,9 +1277,11 @@ void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y
   }
   const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(M.W, [&](auto L, auto I) {
     constexpr int LPR = decltype(L)::value, ITER = decltype(I)::value;
-    const int blocks = grid_for2(M.rows, LPR, sms);
+    const int pf = fast_prefetch();
+    int blocks = grid_for2(M.rows, LPR, sms);
+    if (pf > 0 && blocks > pf * sms) blocks = pf * sms;      // persistent grid: every warp makes several trips and prefetches the next one
     if (nblocks_out) *nblocks_out = blocks;
-    k_spmv2<LPR, ITER, kSpmvRows><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial);
+    k_spmv2<LPR, ITER, kSpmvRows><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, pf > 0);
   });
   if (!done)
     dispatch_lpr(M.W, [&](auto L) {
@@ -1736,7 +1780,10 @@ static void sor_mc_sweep(Grid& g) {
       for (int c = 0; c < ncol_rows; c++) {
         const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
         if (count == 0) continue;
-        k_sor_mc2<LPR, ITER, kMcRows><<<grid_for2(count, LPR, sms, kMcRows), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
+        const int pf = fast_prefetch();
+        int blocks = grid_for2(count, LPR, sms, kMcRows);
+        if (pf > 0 && blocks > pf * sms) blocks = pf * sms;
+        k_sor_mc2<LPR, ITER, kMcRows><<<blocks, kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega, pf > 0);
       }
     });
     if (!done)
@@ -1771,6 +1818,32 @@ void op_sor(Grid& g, int smoother) {
   if (smoother == MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC) {
     MMG_REQUIRE(!g.neumann, MMG_ERR_STATE, "the block-lexicographic smoother is implemented for grids without Neumann boundaries");
     if (!g.have_blocks) build_block_colouring(g);
+  }
+  if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && !g.neumann && L.n_ovf == 0 && g.props.iters >= 1 && !env_int("MMG_MC_PER_COLOUR", 0)) {
+    bool done = false;
+    {
+      TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
+      done = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+        constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+        if (g.colour_ptr_dev.n != g.colour_ptr.size()) g.colour_ptr_dev.upload(g.colour_ptr, g.stream);
+        int blocks_per_sm = 0;
+        MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_mc_all<LPR, ITER, kMcRows>, kBlock, 0));
+        const int sms = sm_count_of(g.device);
+        int maxcount = 0;
+        for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.colour_ptr[c + 1] - g.colour_ptr[c]);
+        int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, kMcRows));
+        HybView A = L.view();
+        const int* rl = g.colour_rows.p;
+        const int* cp = g.colour_ptr_dev.p;
+        int nc = g.n_colours, iters = g.props.iters;
+        const double* b = g.b.p;
+        double* x = g.x.p;
+        double omega = g.props.omega;
+        void* args[] = {&A, &rl, &cp, &nc, &iters, &b, &x, &omega};
+        MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_mc_all<LPR, ITER, kMcRows>, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+      });
+    }
+    if (done) return;
   }
   for (int it = 0; it < g.props.iters; it++) {
     {
@@ -1835,6 +1908,7 @@ void build_colouring(Grid& g) {
   std::vector<int> rows(g.colour_ptr[ncol]), cp(g.colour_ptr.begin(), g.colour_ptr.end() - 1);
   for (int i = 0; i < R; i++) if (colour[i] >= 0) rows[cp[colour[i]]++] = i;
   g.colour_rows.upload(rows, g.stream);
+  g.colour_ptr_dev.upload(g.colour_ptr, g.stream);
   MMG_CUDA(cudaStreamSynchronize(g.stream));
   g.have_colours = true;
 }

@@ -1,0 +1,39 @@
+"""bench.py host logic (no GPU): byte model, level selection and the `--impl reference` arm."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_byte_model_reproduces_baseline_worked_examples():
+    # 4M fine nodes, 6 levels at 4x coarsening, coarse n=25: 52.0 GB (p=6), 30.3 GB (p=4)
+    sides = [63, 125, 250, 500, 1000, 2000]
+    assert abs(bench.algorithmic_bytes_per_cycle(sides, 6) / 1e9 - 52.0) < 1.0
+    assert abs(bench.algorithmic_bytes_per_cycle(sides, 4) / 1e9 - 30.3) < 1.0
+
+
+def test_level_sides():
+    assert bench.level_sides(2000) == [16, 32, 63, 125, 250, 500, 1000, 2000]
+    assert bench.level_sides(1000, 6) == [32, 63, 125, 250, 500, 1000]
+    assert bench.level_sides(100, 4) == [13, 25, 50, 100]
+
+
+def _run(rank):
+    env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank))
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                           "--cpu-side", "40", "--side", "200"], env=env, capture_output=True, text=True, timeout=600)
+
+
+def test_reference_arm_prints_one_line_on_rank0_only():
+    r0, r1 = _run(0), _run(1)
+    assert r0.returncode == 0 and r1.returncode == 0
+    assert r1.stdout.strip() == ""                                     # other ranks exit 0 without work
+    line = json.loads(r0.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "vcycles_per_s" and line["unit"] == "V-cycles/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
+    assert line["higher_is_better"] is True and line["dtype"] == "f64"
