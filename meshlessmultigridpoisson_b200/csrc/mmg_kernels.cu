@@ -1067,36 +1067,153 @@ __device__ __forceinline__ double row_overflow(const HybView& A, int row, int le
   return acc;
 }
 
-template <int LPR, int ITER, int ROWS>
+// ------------------------------------------------------------------------------------------------
+// x-tile staging (third generation).  ncu on the second-generation kernels shows the gathers, not the matrix
+// stream, holding them back: a warp-wide gather of 32 scattered doubles costs up to 32 L1 wavefronts and pulls a
+// 32-byte L2 sector per 8 useful bytes (profiles/r01_sor_mc2_4M_ncu.txt: L1 hit 23 %, DRAM 1.6x the algorithmic
+// bytes).  In the reference's BFS ordering the columns a CTA's rows touch fall into a few short index ranges (arcs of
+// three neighbouring BFS rings), so each CTA (a) loads its rows' chunks, (b) marks the 64-entry blocks of x those
+// columns touch, (c) copies the touched blocks into shared memory with coalesced loads, (d) gathers from shared
+// memory (bank conflicts instead of wavefronts).  No precomputed schedule: the block map is rebuilt per tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStageBlk = 64;          // entries per staged block
+constexpr int kStageMap = 2048;        // blocks covered by the map: 131072 columns from the tile's smallest column
+constexpr int kStageCap = 96;          // staged blocks per tile (48 KB of x)
+constexpr size_t kStageSmem = (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2 + kStageMap + kStageCap * 2 + 64;
+
+struct StageSmem {
+  double* xs;              // kStageCap * 64 staged values
+  unsigned short* blk2off; // per map block: staged slot or 0xFFFF
+  unsigned char* touched;  // per map block
+  unsigned short* list;    // staged slot -> map block
+  int* misc;               // [0] min column, [1] staged count, [2..9] warp scan scratch
+};
+__device__ __forceinline__ StageSmem stage_carve(unsigned char* raw) {
+  StageSmem S;
+  S.xs = reinterpret_cast<double*>(raw);
+  S.blk2off = reinterpret_cast<unsigned short*>(raw + (size_t)kStageCap * kStageBlk * 8);
+  S.touched = raw + (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2;
+  S.list = reinterpret_cast<unsigned short*>(raw + (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2 + kStageMap);
+  S.misc = reinterpret_cast<int*>(raw + (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2 + kStageMap + kStageCap * 2);
+  return S;
+}
+
+// Build the tile's staged copy of x.  Every thread of the CTA calls this with the columns it holds (c[n], -1 = none).
+// Returns the base column of the map.  kBlock threads, 4 block barriers.
+template <int NC>
+__device__ __forceinline__ int stage_build(const StageSmem& S, const int (&c)[NC], const double* x, int xlen) {
+  const int tid = threadIdx.x;
+  if (tid == 0) S.misc[0] = 0x7fffffff;
+  for (int i = tid; i < kStageMap / 8; i += kBlock) reinterpret_cast<unsigned long long*>(S.touched)[i] = 0ull;
+  int mn = 0x7fffffff;
+#pragma unroll
+  for (int n = 0; n < NC; n++) if (c[n] >= 0) mn = min(mn, c[n]);
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  __syncthreads();
+  if ((tid & 31) == 0 && mn != 0x7fffffff) atomicMin(&S.misc[0], mn);
+  __syncthreads();
+  const int cbase = S.misc[0] == 0x7fffffff ? 0 : (S.misc[0] & ~(kStageBlk - 1));
+#pragma unroll
+  for (int n = 0; n < NC; n++)
+    if (c[n] >= 0) { const int blk = (c[n] - cbase) / kStageBlk; if (blk < kStageMap) S.touched[blk] = 1; }
+  __syncthreads();
+  {  // exclusive scan of touched[]: 8 map blocks per thread
+    constexpr int PER = kStageMap / kBlock;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++) cnt += S.touched[tid * PER + j];
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+    if ((tid & 31) == 31) S.misc[2 + (tid >> 5)] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); w++) base += S.misc[2 + w];
+    int run = base + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const int blk = tid * PER + j;
+      if (S.touched[blk]) {
+        if (run < kStageCap) { S.blk2off[blk] = (unsigned short)run; S.list[run] = (unsigned short)blk; }
+        else S.blk2off[blk] = 0xFFFF;
+        run++;
+      } else S.blk2off[blk] = 0xFFFF;
+    }
+    if (tid == kBlock - 1) S.misc[1] = min(run, kStageCap);
+  }
+  __syncthreads();
+  const int staged = S.misc[1];
+  for (int e = tid; e < staged * kStageBlk; e += kBlock) {
+    const int g = cbase + (int)S.list[e / kStageBlk] * kStageBlk + (e % kStageBlk);
+    S.xs[e] = g < xlen ? x[g] : 0.0;
+  }
+  __syncthreads();
+  return cbase;
+}
+__device__ __forceinline__ double stage_read(const StageSmem& S, int cbase, int col, const double* x) {
+  const int rel = col - cbase;
+  const int blk = rel / kStageBlk;
+  if (blk < kStageMap) {
+    const unsigned off = S.blk2off[blk];
+    if (off != 0xFFFFu) return S.xs[off * kStageBlk + (rel % kStageBlk)];
+  }
+  return x[col];
+}
+
+template <int LPR, int ITER, bool SUB, bool DIAG0>
+__device__ __forceinline__ double row_accumulate_staged(const RowRegs<LPR, ITER>& r, const StageSmem& S, int cbase, const double* x, int gl, double& diag) {
+  double acc = 0.0;
+#pragma unroll
+  for (int t = 0; t < ITER; t++) {
+    if (DIAG0 && t == 0 && gl == 0) { diag = r.v[0]; continue; }
+    if (r.c[t] >= 0) {
+      const double p = __dmul_rn(r.v[t], stage_read(S, cbase, r.c[t], x));
+      acc = SUB ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
+    }
+  }
+  return acc;
+}
+
+template <int LPR, int ITER, int ROWS, bool STAGE>
 __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, const double* __restrict__ b, double* y,
                                                   const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
-                                                  double* __restrict__ partial, int prefetch) {
+                                                  double* __restrict__ partial, int xlen) {
+  extern __shared__ __align__(16) unsigned char stage_raw[];
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const unsigned gmask = group_mask<LPR>(lane);
   constexpr int GPW = 32 / LPR;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  constexpr int TR = (kBlock / 32) * GPW * ROWS;       // rows per CTA tile
   const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
+  StageSmem S;
+  if (STAGE) S = stage_carve(stage_raw);
   double num = 0.0, den = 0.0;
-  for (int row0 = warp * GPW * ROWS; row0 < A.rows; row0 += nwarps * GPW * ROWS) {
+  const int ntiles = (A.rows + TR - 1) / TR;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     RowRegs<LPR, ITER> r[ROWS];
     int row[ROWS], len[ROWS];
     bool valid[ROWS];
     double acc[ROWS];
 #pragma unroll
     for (int h = 0; h < ROWS; h++) {
-      row[h] = row0 + h * GPW + lane / LPR;
+      row[h] = tile * TR + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
       valid[h] = row[h] < A.rows;
       row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
     }
-    if (prefetch) {
-#pragma unroll
-      for (int h = 0; h < ROWS; h++) { const int nr = row[h] + nwarps * GPW * ROWS; if (nr < A.rows) prefetch_chunk_l2<LPR>(A, nr, gl); }
-    }
     double dummy;
+    if (STAGE) {
+      int cols[ROWS * ITER];
 #pragma unroll
-    for (int h = 0; h < ROWS; h++) acc[h] = row_accumulate<LPR, ITER, false, false>(r[h], x, keep, gl, dummy);
+      for (int h = 0; h < ROWS; h++)
+#pragma unroll
+        for (int t = 0; t < ITER; t++) cols[h * ITER + t] = r[h].c[t];
+      const int cbase = stage_build<ROWS * ITER>(S, cols, x, xlen);
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) acc[h] = row_accumulate_staged<LPR, ITER, false, false>(r[h], S, cbase, x, gl, dummy);
+    } else {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) acc[h] = row_accumulate<LPR, ITER, false, false>(r[h], x, keep, gl, dummy);
+    }
     if (A.n_ovf) {
 #pragma unroll
       for (int h = 0; h < ROWS; h++) if (valid[h]) acc[h] = row_overflow<LPR, false>(A, row[h], len[h], x, gl, acc[h]);
@@ -1133,38 +1250,44 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, co
   }
 }
 
-template <int LPR, int ITER, int ROWS>
+template <int LPR, int ITER, int ROWS, bool STAGE>
 __device__ __forceinline__ void mc_phase(const HybView& A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
-                                         double omega, int prefetch) {
+                                         double omega, unsigned char* stage_raw, int xlen) {
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const unsigned gmask = group_mask<LPR>(lane);
   constexpr int GPW = 32 / LPR;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  constexpr int TR = (kBlock / 32) * GPW * ROWS;
   const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
-  for (int i0 = warp * GPW * ROWS; i0 < count; i0 += nwarps * GPW * ROWS) {
+  StageSmem S;
+  if (STAGE) S = stage_carve(stage_raw);
+  const int ntiles = (count + TR - 1) / TR;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     RowRegs<LPR, ITER> r[ROWS];
     int row[ROWS], len[ROWS];
     bool valid[ROWS];
     double acc[ROWS], diag[ROWS];
 #pragma unroll
     for (int h = 0; h < ROWS; h++) {
-      const int i = i0 + h * GPW + lane / LPR;
+      const int i = tile * TR + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
       valid[h] = i < count;
       row[h] = valid[h] ? rows_list[i] : 0;
     }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
-    if (prefetch) {
+    if (STAGE) {
+      int cols[ROWS * ITER];
 #pragma unroll
-      for (int h = 0; h < ROWS; h++) {
-        const int ni = i0 + nwarps * GPW * ROWS + h * GPW + lane / LPR;
-        if (ni < count) prefetch_chunk_l2<LPR>(A, rows_list[ni], gl);
-      }
+      for (int h = 0; h < ROWS; h++)
+#pragma unroll
+        for (int t = 0; t < ITER; t++) cols[h * ITER + t] = r[h].c[t];
+      const int cbase = stage_build<ROWS * ITER>(S, cols, x, xlen);
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate_staged<LPR, ITER, true, true>(r[h], S, cbase, x, gl, diag[h]); }
+    } else {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate<LPR, ITER, true, true>(r[h], x, keep, gl, diag[h]); }
     }
-#pragma unroll
-    for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate<LPR, ITER, true, true>(r[h], x, keep, gl, diag[h]); }
     if (A.n_ovf) {
 #pragma unroll
       for (int h = 0; h < ROWS; h++) if (valid[h]) acc[h] = row_overflow<LPR, true>(A, row[h], len[h], x, gl, acc[h]);
@@ -1185,24 +1308,26 @@ __device__ __forceinline__ void mc_phase(const HybView& A, const int* __restrict
   }
 }
 
-template <int LPR, int ITER, int ROWS>
+template <int LPR, int ITER, int ROWS, bool STAGE>
 __global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
-                                                    double omega, int prefetch) {
-  mc_phase<LPR, ITER, ROWS>(A, rows_list, count, b, x, omega, prefetch);
+                                                    double omega, int xlen) {
+  extern __shared__ __align__(16) unsigned char stage_raw[];
+  mc_phase<LPR, ITER, ROWS, STAGE>(A, rows_list, count, b, x, omega, stage_raw, xlen);
 }
 
 // All colours of all `iters` sweeps of a grid without Neumann rows in ONE cooperative launch, a grid-wide barrier
 // between colour phases.  On the coarse levels a colour phase is a few microseconds of work, so per-colour launches
 // were launch-gap bound (ncu launch list, profiles/r01_launches_mc_4M_summary.txt: the W=25 levels took 44 % of the
 // cycle in 2100 launches).
-template <int LPR, int ITER, int ROWS>
+template <int LPR, int ITER, int ROWS, bool STAGE>
 __global__ void __launch_bounds__(kBlock) k_sor_mc_all(HybView A, const int* __restrict__ rows_list, const int* __restrict__ colour_ptr, int ncolours,
-                                                       int iters, const double* __restrict__ b, double* x, double omega) {
+                                                       int iters, const double* __restrict__ b, double* x, double omega, int xlen) {
+  extern __shared__ __align__(16) unsigned char stage_raw[];
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   for (int it = 0; it < iters; it++)
     for (int c = 0; c < ncolours; c++) {
       const int first = colour_ptr[c], count = colour_ptr[c + 1] - first;
-      mc_phase<LPR, ITER, ROWS>(A, rows_list + first, count, b, x, omega, 0);
+      mc_phase<LPR, ITER, ROWS, STAGE>(A, rows_list + first, count, b, x, omega, stage_raw, xlen);
       grid.sync();
     }
 }
@@ -1259,8 +1384,11 @@ bool dispatch_lpr_iter(int W, F&& f) {
 #undef MMG_CASE
   return false;
 }
-// MMG_FAST_PREFETCH=n: persistent grid of n CTAs per SM with next-trip L2 prefetch (0 = one trip per warp, no prefetch)
-int fast_prefetch() { static int v = -2; if (v == -2) { const char* e = getenv("MMG_FAST_PREFETCH"); v = e ? atoi(e) : 0; } return v; }
+// MMG_FAST_STAGE=1 turns the shared-memory x-tile staging on.  Off by default: measured 3x SLOWER than the
+// second-generation L2 gathers (784 vs 2515 GB/s on the 4M-node sweep) — four block barriers and a 2048-entry map scan
+// per 64-row tile serialise the HBM latency of the chunk loads with the staging loads.  Kept as the starting point for
+// a precomputed-segment, double-buffered version.
+int fast_stage() { static int v = -2; if (v == -2) { const char* e = getenv("MMG_FAST_STAGE"); v = e ? atoi(e) : 0; } return v; }
 constexpr int kSpmvRows = MMG_FAST_ROWS;   // rows in flight per lane group: 4 is best for the streaming SpMV kernels (profiles/r01_kernel_rates.txt)
 constexpr int kMcRows = 2;                 // ... and 2 for the multicolour sweep, whose gathers do not coalesce
 int grid_for2(int rows, int lpr, int sm_count, int per = kSpmvRows) { return grid_for((rows + per - 1) / per, lpr, sm_count); }
@@ -1277,11 +1405,16 @@ void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y
   }
   const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(M.W, [&](auto L, auto I) {
     constexpr int LPR = decltype(L)::value, ITER = decltype(I)::value;
-    const int pf = fast_prefetch();
     int blocks = grid_for2(M.rows, LPR, sms);
-    if (pf > 0 && blocks > pf * sms) blocks = pf * sms;      // persistent grid: every warp makes several trips and prefetches the next one
     if (nblocks_out) *nblocks_out = blocks;
-    k_spmv2<LPR, ITER, kSpmvRows><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, pf > 0);
+    if (fast_stage()) {
+      auto kern = k_spmv2<LPR, ITER, kSpmvRows, true>;
+      static bool configured = false;
+      if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem)); configured = true; }
+      kern<<<blocks, kBlock, kStageSmem, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols);
+    } else {
+      k_spmv2<LPR, ITER, kSpmvRows, false><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols);
+    }
   });
   if (!done)
     dispatch_lpr(M.W, [&](auto L) {
@@ -1780,10 +1913,15 @@ static void sor_mc_sweep(Grid& g) {
       for (int c = 0; c < ncol_rows; c++) {
         const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
         if (count == 0) continue;
-        const int pf = fast_prefetch();
-        int blocks = grid_for2(count, LPR, sms, kMcRows);
-        if (pf > 0 && blocks > pf * sms) blocks = pf * sms;
-        k_sor_mc2<LPR, ITER, kMcRows><<<blocks, kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega, pf > 0);
+        const int blocks = grid_for2(count, LPR, sms, kMcRows);
+        if (fast_stage()) {
+          auto kern = k_sor_mc2<LPR, ITER, kMcRows, true>;
+          static bool configured = false;
+          if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem)); configured = true; }
+          kern<<<blocks, kBlock, kStageSmem, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega, g.A);
+        } else {
+          k_sor_mc2<LPR, ITER, kMcRows, false><<<blocks, kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega, g.A);
+        }
       }
     });
     if (!done)
@@ -1826,8 +1964,13 @@ void op_sor(Grid& g, int smoother) {
       done = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
         constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
         if (g.colour_ptr_dev.n != g.colour_ptr.size()) g.colour_ptr_dev.upload(g.colour_ptr, g.stream);
+        const bool stage = fast_stage() != 0;
+        void* kern = stage ? (void*)k_sor_mc_all<LPR, ITER, kMcRows, true> : (void*)k_sor_mc_all<LPR, ITER, kMcRows, false>;
+        const size_t smem = stage ? kStageSmem : 0;
+        static bool configured = false;
+        if (stage && !configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem)); configured = true; }
         int blocks_per_sm = 0;
-        MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_mc_all<LPR, ITER, kMcRows>, kBlock, 0));
+        MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, smem));
         const int sms = sm_count_of(g.device);
         int maxcount = 0;
         for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.colour_ptr[c + 1] - g.colour_ptr[c]);
@@ -1839,8 +1982,9 @@ void op_sor(Grid& g, int smoother) {
         const double* b = g.b.p;
         double* x = g.x.p;
         double omega = g.props.omega;
-        void* args[] = {&A, &rl, &cp, &nc, &iters, &b, &x, &omega};
-        MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_mc_all<LPR, ITER, kMcRows>, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+        int xlen = g.A;
+        void* args[] = {&A, &rl, &cp, &nc, &iters, &b, &x, &omega, &xlen};
+        MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, smem, g.stream));
       });
     }
     if (done) return;
