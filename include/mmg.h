@@ -152,6 +152,16 @@ int mmg_solver_launch_count(mmg_solver* s, int64_t* launches);                  
 /* CUDA-event timed V-cycles on the solver's stream: runs n cycles, returns elapsed device ms */
 int mmg_solver_time_vcycles(mmg_solver* s, int n_cycles, double* ms);
 
+/* ---------------------------------------------------------------- multi-GPU (no reference counterpart: the reference is serial) ---
+ * One process per GPU.  Levels with at least `threshold` rows are cut into contiguous row blocks in the reference order
+ * (rank r owns rows [bounds[r], bounds[r+1])); each rank sweeps only its block and exchanges the index ranges its rows read
+ * with grouped ncclSend/ncclRecv; smaller levels are replicated.  Needs the multicolour smoother with fast arithmetic. */
+int mmg_partition_bounds(int n, int world, int* bounds);                           /* the partition map (world+1 offsets), pure host */
+int mmg_comm_unique_id(char* out128);                                              /* ncclGetUniqueId on rank 0; ship the 128 bytes to every rank */
+int mmg_solver_init_comm(mmg_solver* s, int rank, int world, const char* id128);   /* ncclCommInitRank on the solver's device */
+int mmg_solver_set_partition_threshold(mmg_solver* s, int rows);
+int mmg_solver_comm_stats(mmg_solver* s, int64_t* messages, int64_t* bytes_sent, int* partitioned_levels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mmg_kernels.cu", "mmg_assembly.cu", "mmg_api.cu"]
+SOURCES = ["mmg_kernels.cu", "mmg_assembly.cu", "mmg_api.cu", "mmg_comm.cu"]
 LIB = os.path.join(HERE, "libmmg.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-lcudart", "-ccbin", "/usr/bin/g++"])
+    subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl", "-ccbin", "/usr/bin/g++"])
     return LIB
 
 

@@ -112,6 +112,11 @@ SIGNATURES = {
     "mmg_solver_reset_timers": [_vp],
     "mmg_solver_launch_count": [_vp, C.POINTER(C.c_int64)],
     "mmg_solver_time_vcycles": [_vp, _i, C.POINTER(_d)],
+    "mmg_partition_bounds": [_i, _i, _ip],
+    "mmg_comm_unique_id": [C.c_char_p],
+    "mmg_solver_init_comm": [_vp, _i, _i, C.c_char_p],
+    "mmg_solver_set_partition_threshold": [_vp, _i],
+    "mmg_solver_comm_stats": [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_i)],
 }
 _NON_STATUS = {"mmg_last_error": (C.c_char_p, []), "mmg_build_info": (C.c_char_p, [])}
 
@@ -503,10 +508,36 @@ class Multigrid:
         _ck(self.L, self.L.mmg_solver_launch_count(self.h, n))
         return n.value
 
+    def init_comm(self, rank, world, unique_id):
+        _ck(self.L, self.L.mmg_solver_init_comm(self.h, rank, world, unique_id))
+
+    def set_partition_threshold(self, rows):
+        _ck(self.L, self.L.mmg_solver_set_partition_threshold(self.h, rows))
+
+    def comm_stats(self):
+        m, b, p = C.c_int64(), C.c_int64(), _i()
+        _ck(self.L, self.L.mmg_solver_comm_stats(self.h, m, b, p))
+        return dict(messages=m.value, bytes_sent=b.value, partitioned_levels=p.value)
+
     def time_vcycles(self, n):
         ms = _d()
         _ck(self.L, self.L.mmg_solver_time_vcycles(self.h, n, ms))
         return ms.value
+
+
+def partition_bounds(n, world):
+    """rank r owns rows [bounds[r], bounds[r+1]) — contiguous blocks whose sizes differ by at most one (pure host logic)."""
+    L = load()
+    b = np.empty(world + 1, np.int32)
+    _ck(L, L.mmg_partition_bounds(n, world, b))
+    return b
+
+
+def comm_unique_id():
+    L = load()
+    buf = C.create_string_buffer(128)
+    _ck(L, L.mmg_comm_unique_id(buf))
+    return buf.raw
 
 
 class FractionalStepMultigrid(Multigrid):

@@ -15,6 +15,7 @@ Grid::~Grid() {
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 Solver::~Solver() {
+  comm_destroy(*this);
   for (Grid* g : grids) delete g;
   for (HybMatrix* m : restrict_) delete m;
   for (HybMatrix* m : prolong_) delete m;
@@ -155,7 +156,10 @@ static void vcycle(Solver& s) {
     MMG_CUDA(cudaStreamSynchronize(s.stream));
     s.hist = std::move(bigger);
   }
-  op_residual_norm(*cur, s.hist.p + s.hist_len);   // residuals_.push_back(residual()), :66-67
+  const bool dist = s.world > 1;
+  if (dist && !s.dist_ready) dist_setup(s);
+  if (dist) dist_residual_norm(s, (int)L - 1, s.hist.p + s.hist_len);
+  else op_residual_norm(*cur, s.hist.p + s.hist_len);   // residuals_.push_back(residual()), :66-67
   s.hist_len++;
   op_bound_eval_neumann(*cur);                      // :68
   for (size_t i = L - 1; i > 0; i--) {              // :71-88
@@ -163,19 +167,24 @@ static void vcycle(Solver& s) {
     Grid* coarse = s.grids[i - 1];
     if (i != L - 1) op_zero_values(*cur);
     op_boundary_op(*cur, i == L - 1 ? MMG_FINE : MMG_COARSE);
-    op_sor(*cur, s.smoother);
-    op_residual(*cur, cur->r.p);
-    op_restrict(*cur, *coarse, *s.restrict_[i], cur->r.p);
+    if (dist) { dist_sor(s, (int)i); dist_residual(s, (int)i); dist_restrict(s, (int)i); }
+    else {
+      op_sor(*cur, s.smoother);
+      op_residual(*cur, cur->r.p);
+      op_restrict(*cur, *coarse, *s.restrict_[i], cur->r.p);
+    }
   }
   op_boundary_op(*cur, MMG_COARSE);                 // quirk kept: still grid 1 (or the only grid), :91
   cur = s.grids[0];
   op_zero_values(*cur);
-  op_sor(*cur, s.smoother);
-  op_sor(*cur, s.smoother);
+  if (dist) { dist_sor(s, 0); dist_sor(s, 0); } else { op_sor(*cur, s.smoother); op_sor(*cur, s.smoother); }
   for (size_t i = 1; i < L; i++) {                  // :99-109
     cur = s.grids[i];
-    op_prolong_correct(*cur, *s.grids[i - 1], *s.prolong_[i - 1]);
-    op_sor(*cur, s.smoother);
+    if (dist) { dist_prolong_correct(s, (int)i); dist_sor(s, (int)i); }
+    else {
+      op_prolong_correct(*cur, *s.grids[i - 1], *s.prolong_[i - 1]);
+      op_sor(*cur, s.smoother);
+    }
   }
 }
 
@@ -800,7 +809,8 @@ int mmg_solver_residual(mmg_solver* s, double* out) {
   use_device(fine.device);
   DevBuf<double> ratio;
   ratio.alloc(1);
-  op_residual_norm(fine, ratio.p);
+  if (so.world > 1) { if (!so.dist_ready) dist_setup(so); dist_residual_norm(so, (int)so.grids.size() - 1, ratio.p); }
+  else op_residual_norm(fine, ratio.p);
   ratio.download(out, 1, so.stream);
   API_END
 }
@@ -831,7 +841,8 @@ int mmg_solver_solve(mmg_solver* s, double tol, int max_cycles, int extra_bound_
   int n = 0;
   double r = 0;
   while (true) {                       // while (mg.residual() >= tol) { mg.vCycle(); [bound_eval_neumann();] }
-    op_residual_norm(fine, ratio.p);
+    if (so.world > 1) { if (!so.dist_ready) dist_setup(so); dist_residual_norm(so, (int)so.grids.size() - 1, ratio.p); }
+    else op_residual_norm(fine, ratio.p);
     ratio.download(&r, 1, so.stream);
     if (!(r >= tol) || n >= max_cycles) break;
     vcycle(so);
@@ -887,6 +898,57 @@ int mmg_solver_reset_timers(mmg_solver* s) {
 int mmg_debug_lex_trace(long long* out, int n) {
   API_BEGIN
   mmg::debug_lex_trace(out, n);
+  API_END
+}
+// ---------------------------------------------------------------------------------------------- multi-GPU
+int mmg_partition_bounds(int n, int world, int* bounds) {
+  API_BEGIN
+  NEED(bounds);
+  MMG_REQUIRE(n >= 0 && world >= 1, MMG_ERR_ARG, "partition_bounds: bad sizes");
+  partition_bounds(n, world, bounds);
+  API_END
+}
+int mmg_comm_unique_id(char* out128) {
+  API_BEGIN
+  NEED(out128);
+  comm_unique_id(out128);
+  API_END
+}
+int mmg_solver_init_comm(mmg_solver* s, int rank, int world, const char* id128) {
+  API_BEGIN
+  NEED(s);
+  MMG_REQUIRE(world == 1 || id128 != nullptr, MMG_ERR_ARG, "init_comm: the NCCL unique id is missing");
+  use_device(S(s).grids.empty() ? 0 : S(s).grids[0]->device);
+  comm_init(S(s), rank, world, id128);
+  S(s).dist_ready = false;
+  API_END
+}
+int mmg_solver_set_partition_threshold(mmg_solver* s, int rows) {
+  API_BEGIN
+  NEED(s);
+  S(s).part_threshold = rows;
+  S(s).dist_ready = false;
+  API_END
+}
+int mmg_solver_comm_stats(mmg_solver* s, int64_t* messages, int64_t* bytes_sent, int* partitioned_levels) {
+  API_BEGIN
+  NEED(s);
+  if (messages) *messages = S(s).comm_msgs;
+  if (bytes_sent) *bytes_sent = S(s).comm_bytes;
+  if (partitioned_levels) { int n = 0; for (const LevelDist& d : S(s).dist) n += d.partitioned; *partitioned_levels = n; }
+  API_END
+}
+// diagnostics (not in include/mmg.h): the exchange plan a rank derives from everybody's need intervals; pure host logic
+int mmg_debug_exchange_plan(int rank, int world, const int* need, const int* bounds, int* n_send, int* sends, int* n_recv, int* recvs) {
+  API_BEGIN
+  std::vector<std::pair<int, int>> nd(world);
+  for (int r = 0; r < world; r++) nd[r] = {need[2 * r], need[2 * r + 1]};
+  std::vector<int> b(bounds, bounds + world + 1);
+  ExchangePlan P;
+  plan_build(P, rank, world, nd, b);
+  *n_send = (int)P.sends.size(); *n_recv = (int)P.recvs.size();
+  for (size_t i = 0; i < P.sends.size(); i++) { sends[3 * i] = P.sends[i].peer; sends[3 * i + 1] = P.sends[i].offset; sends[3 * i + 2] = P.sends[i].count; }
+  for (size_t i = 0; i < P.recvs.size(); i++) { recvs[3 * i] = P.recvs[i].peer; recvs[3 * i + 1] = P.recvs[i].offset; recvs[3 * i + 2] = P.recvs[i].count; }
   API_END
 }
 int mmg_solver_launch_count(mmg_solver* s, int64_t* launches) {

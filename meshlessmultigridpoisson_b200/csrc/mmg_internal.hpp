@@ -176,6 +176,7 @@ struct Grid {
   DevBuf<int> colour_rows;               // rows grouped by colour, ascending inside a colour
   DevBuf<int> colour_ptr_dev;            // colour_ptr on the device (persistent multicolour kernel)
   std::vector<int> colour_host;          // per-row colour (-1 skipped)
+  std::vector<int> colour_rows_host;     // host copy of colour_rows (multi-GPU sub-ranges)
   // block-lexicographic schedule
   int block_size = 4096;
   bool have_blocks = false;
@@ -189,8 +190,31 @@ struct Grid {
   void sync() { MMG_CUDA(cudaStreamSynchronize(stream)); }
 };
 
+// halo exchange of contiguous index ranges of a full-length vector
+struct ExchangePlan {
+  struct Msg { int peer, offset, count; };
+  std::vector<Msg> sends, recvs;
+};
+// how one level is spread over the ranks: contiguous row blocks in the reference order
+struct LevelDist {
+  bool partitioned = false;
+  std::vector<int> bounds;                       // world+1 row offsets: rank r owns [bounds[r], bounds[r+1])
+  ExchangePlan x_plan;                           // entries of values_ that my rows of laplaceMat_ read from other ranks
+  std::vector<int> r_bounds;                     // split of the restriction's OUTPUT rows (coarse rows of level-1) among ranks
+  ExchangePlan r_plan;                           // entries of this level's residual that my restriction rows read
+  ExchangePlan p_plan;                           // entries of the coarser level's values_ that my prolongation rows read
+  std::vector<std::pair<int, int>> colour_sub;   // per colour: (first, count) of my rows inside colour_rows
+};
+
 struct Solver {
   int flavour = MMG_FLAVOUR_MULTIGRID;
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  int64_t comm_msgs = 0, comm_bytes = 0;
+  int part_threshold = 200000;                   // levels with fewer rows are replicated on every rank
+  bool dist_ready = false;
+  std::vector<LevelDist> dist;
+  DevBuf<double> sums;                           // [num, den] of the distributed residual norm
   int smoother = MMG_SMOOTHER_LEXICOGRAPHIC;
   int arithmetic = MMG_ARITH_REFERENCE_ORDER;
   std::vector<Grid*> grids;                 // sorted ascending by (size, pointer), like multigrid.cpp:116-122
@@ -239,5 +263,21 @@ struct TimedScope {
 };
 void timers_collect(Timers& t);
 void debug_lex_trace(long long* out, int n);
+
+// ---- multi-GPU (comm.cu, kernels.cu) ---------------------------------------------------------------
+void partition_bounds(int n, int world, int* bounds);
+void comm_unique_id(char* out128);
+void comm_init(Solver& s, int rank, int world, const char* id128);
+void comm_destroy(Solver& s);
+void plan_build(ExchangePlan& P, int rank, int world, const std::vector<std::pair<int, int>>& need, const std::vector<int>& bounds);
+void plan_execute(Solver& s, const ExchangePlan& P, double* vec);
+void allgather_blocks(Solver& s, double* vec, const std::vector<int>& bounds);
+void allreduce_sum(Solver& s, double* dev, int count);
+void dist_setup(Solver& s);
+void dist_residual_norm(Solver& s, int level, double* ratio_dev);
+void dist_residual(Solver& s, int level);
+void dist_sor(Solver& s, int level);
+void dist_restrict(Solver& s, int level);
+void dist_prolong_correct(Solver& s, int level);
 
 }  // namespace mmg

@@ -1177,7 +1177,7 @@ __device__ __forceinline__ double row_accumulate_staged(const RowRegs<LPR, ITER>
 template <int LPR, int ITER, int ROWS, bool STAGE>
 __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, const double* __restrict__ b, double* y,
                                                   const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
-                                                  double* __restrict__ partial, int xlen) {
+                                                  double* __restrict__ partial, int xlen, int row0, int nrows) {
   extern __shared__ __align__(16) unsigned char stage_raw[];
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
@@ -1188,7 +1188,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, co
   StageSmem S;
   if (STAGE) S = stage_carve(stage_raw);
   double num = 0.0, den = 0.0;
-  const int ntiles = (A.rows + TR - 1) / TR;
+  const int ntiles = (nrows + TR - 1) / TR;            // rows [row0, row0+nrows): the whole matrix, or this rank's block
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     RowRegs<LPR, ITER> r[ROWS];
     int row[ROWS], len[ROWS];
@@ -1196,8 +1196,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, co
     double acc[ROWS];
 #pragma unroll
     for (int h = 0; h < ROWS; h++) {
-      row[h] = tile * TR + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
-      valid[h] = row[h] < A.rows;
+      row[h] = row0 + tile * TR + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
+      valid[h] = row[h] < row0 + nrows;
       row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
     }
     double dummy;
@@ -1394,8 +1394,10 @@ constexpr int kMcRows = 2;                 // ... and 2 for the multicolour swee
 int grid_for2(int rows, int lpr, int sm_count, int per = kSpmvRows) { return grid_for((rows + per - 1) / per, lpr, sm_count); }
 
 void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
-                 double* partial, int* nblocks_out, int device, cudaStream_t s, bool exact) {
+                 double* partial, int* nblocks_out, int device, cudaStream_t s, bool exact, int row0 = 0, int nrows = -1) {
   const int sms = sm_count_of(device);
+  if (nrows < 0) nrows = M.rows;
+  MMG_REQUIRE(!exact || (row0 == 0 && nrows == M.rows), MMG_ERR_STATE, "row-block launches exist for the fast-arithmetic kernels only");
   if (exact) {
     const int blocks = grid_for(M.rows, 32, sms);
     if (nblocks_out) *nblocks_out = blocks;
@@ -1405,17 +1407,18 @@ void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y
   }
   const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(M.W, [&](auto L, auto I) {
     constexpr int LPR = decltype(L)::value, ITER = decltype(I)::value;
-    int blocks = grid_for2(M.rows, LPR, sms);
+    int blocks = grid_for2(nrows, LPR, sms);
     if (nblocks_out) *nblocks_out = blocks;
     if (fast_stage()) {
       auto kern = k_spmv2<LPR, ITER, kSpmvRows, true>;
       static bool configured = false;
       if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem)); configured = true; }
-      kern<<<blocks, kBlock, kStageSmem, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols);
+      kern<<<blocks, kBlock, kStageSmem, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols, row0, nrows);
     } else {
-      k_spmv2<LPR, ITER, kSpmvRows, false><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols);
+      k_spmv2<LPR, ITER, kSpmvRows, false><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols, row0, nrows);
     }
   });
+  MMG_REQUIRE(done || (row0 == 0 && nrows == M.rows), MMG_ERR_STATE, "row-block launch: stencil width outside the fast kernels' table");
   if (!done)
     dispatch_lpr(M.W, [&](auto L) {
       constexpr int LPR = decltype(L)::value;
@@ -2006,6 +2009,172 @@ void debug_lex_trace(long long* out, int n) {
   MMG_CUDA(cudaMemcpyFromSymbol(out, g_lex_trace, sizeof(long long) * std::min(n, 16 * 64)));
 }
 
+// ================================================================================================
+// Multi-GPU: row-block partition of the large levels, halo exchange of contiguous ranges
+// ================================================================================================
+namespace {
+__global__ void __launch_bounds__(kBlock) k_col_range(HybView A, int row0, int nrows, int* out2) {
+  int mn = 0x7fffffff, mx = -1;
+  for (int r = row0 + blockIdx.x * blockDim.x + threadIdx.x; r < row0 + nrows; r += gridDim.x * blockDim.x) {
+    const int len = A.len[r];
+    const int* __restrict__ c = row_col(A, r);
+    const int m = len < A.W ? len : A.W;
+    for (int k = 0; k < m; k++) { mn = min(mn, c[k]); mx = max(mx, c[k]); }
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) { atomicMin(out2, mn); atomicMax(out2 + 1, mx); }
+}
+__global__ void k_ratio(const double* sums, double* ratio) { *ratio = sums[0] / sums[1]; }
+__global__ void __launch_bounds__(kBlock) k_sum_partials(const double* __restrict__ partial, int n, double* sums) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+  block_sum2(a, b);
+  if (threadIdx.x == 0) { sums[0] = a; sums[1] = b; }
+}
+
+// [min col, max col + 1) over rows [row0, row0+nrows) of M, for every rank's block
+std::vector<std::pair<int, int>> column_needs(Grid& ctx, const HybMatrix& M, const std::vector<int>& row_bounds) {
+  MMG_REQUIRE(M.n_ovf == 0 && M.reg_row < 0, MMG_ERR_STATE, "multi-GPU partition supports operators without spill rows (Dirichlet grids)");
+  const int world = (int)row_bounds.size() - 1;
+  DevBuf<int> out;
+  out.alloc(2 * world);
+  std::vector<int> init(2 * world);
+  for (int r = 0; r < world; r++) { init[2 * r] = 0x7fffffff; init[2 * r + 1] = -1; }
+  out.upload(init, ctx.stream);
+  for (int r = 0; r < world; r++) {
+    const int n = row_bounds[r + 1] - row_bounds[r];
+    if (n > 0) k_col_range<<<std::min(1024, (n + kBlock - 1) / kBlock), kBlock, 0, ctx.stream>>>(M.view(), row_bounds[r], n, out.p + 2 * r);
+  }
+  MMG_CUDA(cudaGetLastError());
+  std::vector<int> h = out.to_host(ctx.stream);
+  std::vector<std::pair<int, int>> need(world);
+  for (int r = 0; r < world; r++) need[r] = h[2 * r + 1] < 0 ? std::make_pair(0, 0) : std::make_pair(h[2 * r], h[2 * r + 1] + 1);
+  return need;
+}
+}  // namespace
+
+void dist_setup(Solver& s) {
+  const int L = (int)s.grids.size(), W = s.world;
+  s.dist.assign(L, LevelDist());
+  if (s.sums.n < 2) s.sums.alloc(2);
+  for (int l = 0; l < L; l++) {
+    Grid& g = *s.grids[l];
+    LevelDist& D = s.dist[l];
+    MMG_REQUIRE(!g.neumann, MMG_ERR_STATE, "multi-GPU partition is implemented for grids without Neumann boundaries");
+    D.partitioned = W > 1 && g.n >= s.part_threshold;
+    D.bounds.resize(W + 1);
+    partition_bounds(g.n, W, D.bounds.data());
+    if (!D.partitioned) continue;
+    plan_build(D.x_plan, s.rank, W, column_needs(g, g.Lap, D.bounds), D.bounds);
+    if (!g.have_colours) build_colouring(g);
+    D.colour_sub.resize(g.n_colours);
+    for (int c = 0; c < g.n_colours; c++) {
+      const int* b = g.colour_rows_host.data() + g.colour_ptr[c];
+      const int* e = g.colour_rows_host.data() + g.colour_ptr[c + 1];
+      const int* lo = std::lower_bound(b, e, D.bounds[s.rank]);
+      const int* hi = std::lower_bound(b, e, D.bounds[s.rank + 1]);
+      D.colour_sub[c] = {(int)(lo - g.colour_rows_host.data()), (int)(hi - lo)};
+    }
+  }
+  for (int l = 1; l < L; l++) {
+    LevelDist& D = s.dist[l];
+    if (!D.partitioned) continue;
+    Grid& fine = *s.grids[l];
+    Grid& coarse = *s.grids[l - 1];
+    // restriction: its output rows (coarse rows) are split like the coarse level's vectors; it reads this level's residual
+    D.r_bounds = s.dist[l - 1].bounds;
+    plan_build(D.r_plan, s.rank, W, column_needs(fine, *s.restrict_[l], D.r_bounds), D.bounds);
+    // prolongation: output rows = my rows of this level; it reads the coarser level's values_
+    if (s.dist[l - 1].partitioned) plan_build(D.p_plan, s.rank, W, column_needs(fine, *s.prolong_[l - 1], D.bounds), s.dist[l - 1].bounds);
+    (void)coarse;
+  }
+  s.dist_ready = true;
+}
+
+void dist_residual(Solver& s, int level) {
+  Grid& g = *s.grids[level];
+  const LevelDist& D = s.dist[level];
+  if (!D.partitioned) { op_residual(g, g.r.p); return; }
+  const int lo = D.bounds[s.rank], n = D.bounds[s.rank + 1] - lo;
+  TimedScope ts(g, MMG_T_RESIDUAL, (g.Lap.matrix_bytes() + (int64_t)g.A * 24) / s.world, 1);
+  launch_spmv(g.Lap, g.x.p, g.b.p, g.r.p, g.rowflag.p, OP_RESID, 0, 0, nullptr, nullptr, g.device, g.stream, false, lo, n);
+}
+
+void dist_residual_norm(Solver& s, int level, double* ratio_dev) {
+  Grid& g = *s.grids[level];
+  const LevelDist& D = s.dist[level];
+  if (!D.partitioned) { op_residual_norm(g, ratio_dev); return; }
+  const int lo = D.bounds[s.rank], n = D.bounds[s.rank + 1] - lo;
+  ensure_partials(g, (size_t)2 * (sm_count_of(g.device) * 32 + 8) + kRegBlocks);
+  int nb = 0;
+  {
+    TimedScope ts(g, MMG_T_RESIDUAL, (g.Lap.matrix_bytes() + (int64_t)g.A * 24) / s.world, 3);
+    launch_spmv(g.Lap, g.x.p, g.b.p, nullptr, g.rowflag.p, OP_RESID, 0, 0, g.partials.p, &nb, g.device, g.stream, false, lo, n);
+    k_sum_partials<<<1, kBlock, 0, g.stream>>>(g.partials.p, nb, s.sums.p);
+    MMG_CUDA(cudaGetLastError());
+  }
+  allreduce_sum(s, s.sums.p, 2);
+  k_ratio<<<1, 1, 0, g.stream>>>(s.sums.p, ratio_dev);
+  MMG_CUDA(cudaGetLastError());
+}
+
+void dist_sor(Solver& s, int level) {
+  Grid& g = *s.grids[level];
+  const LevelDist& D = s.dist[level];
+  if (!D.partitioned) { op_sor(g, s.smoother); return; }
+  MMG_REQUIRE(s.smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact, MMG_ERR_STATE,
+              "a partitioned level needs the multicolour smoother with fast arithmetic: the lexicographic sweep is a pipeline across ranks, not a partition");
+  const HybMatrix& L = g.Lap;
+  const int sms = sm_count_of(g.device);
+  for (int it = 0; it < g.props.iters; it++) {
+    TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) / s.world, g.n_colours);
+    for (int c = 0; c < g.n_colours; c++) {
+      const int first = D.colour_sub[c].first, count = D.colour_sub[c].second;
+      if (count > 0) {
+        const bool ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+          constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+          k_sor_mc2<LPR, ITER, kMcRows, false><<<grid_for2(count, LPR, sms, kMcRows), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p,
+                                                                                                           g.x.p, g.props.omega, g.A);
+        });
+        MMG_REQUIRE(ok, MMG_ERR_STATE, "stencil width outside the fast kernels' table");
+      }
+      plan_execute(s, D.x_plan, g.x.p);     // neighbours need this colour's new values before their next phase
+    }
+    MMG_CUDA(cudaGetLastError());
+  }
+}
+
+void dist_restrict(Solver& s, int level) {
+  Grid& fine = *s.grids[level];
+  Grid& coarse = *s.grids[level - 1];
+  const LevelDist& D = s.dist[level];
+  if (!D.partitioned) { op_restrict(fine, coarse, *s.restrict_[level], fine.r.p); return; }
+  const HybMatrix& R = *s.restrict_[level];
+  plan_execute(s, D.r_plan, fine.r.p);
+  const int lo = D.r_bounds[s.rank], n = D.r_bounds[s.rank + 1] - lo;
+  {
+    TimedScope ts(fine, MMG_T_RESTRICT, (R.matrix_bytes() + (int64_t)coarse.n * 8 + (int64_t)fine.n * 8) / s.world, 1);
+    if (n > 0) launch_spmv(R, fine.r.p, nullptr, coarse.b.p, coarse.rowflag.p, OP_RESTRICT, 1, 0, nullptr, nullptr, fine.device, fine.stream, false, lo, n);
+  }
+  if (!s.dist[level - 1].partitioned) allgather_blocks(s, coarse.b.p, D.r_bounds);   // the coarser level is replicated: everyone needs all of its source
+}
+
+void dist_prolong_correct(Solver& s, int level) {
+  Grid& fine = *s.grids[level];
+  Grid& coarse = *s.grids[level - 1];
+  const LevelDist& D = s.dist[level];
+  if (!D.partitioned) { op_prolong_correct(fine, coarse, *s.prolong_[level - 1]); return; }
+  const HybMatrix& P = *s.prolong_[level - 1];
+  if (s.dist[level - 1].partitioned) plan_execute(s, D.p_plan, coarse.x.p);
+  const int lo = D.bounds[s.rank], n = D.bounds[s.rank + 1] - lo;
+  {
+    TimedScope ts(fine, MMG_T_PROLONG, (P.matrix_bytes() + (int64_t)fine.n * 16 + (int64_t)coarse.n * 8) / s.world, 1);
+    launch_spmv(P, coarse.x.p, nullptr, fine.x.p, fine.rowflag.p, OP_PROLONG, 1, 0, nullptr, nullptr, fine.device, fine.stream, false, lo, n);
+  }
+  plan_execute(s, D.x_plan, fine.x.p);      // corrected values next to the cut
+}
+
 // ---- schedules (integer artefacts) ----------------------------------------------------------------
 void build_colouring(Grid& g) {
   // First-fit in ascending row order on the structurally symmetrised graph of the rows the sweep visits;
@@ -2052,6 +2221,7 @@ void build_colouring(Grid& g) {
   std::vector<int> rows(g.colour_ptr[ncol]), cp(g.colour_ptr.begin(), g.colour_ptr.end() - 1);
   for (int i = 0; i < R; i++) if (colour[i] >= 0) rows[cp[colour[i]]++] = i;
   g.colour_rows.upload(rows, g.stream);
+  g.colour_rows_host = rows;
   g.colour_ptr_dev.upload(g.colour_ptr, g.stream);
   MMG_CUDA(cudaStreamSynchronize(g.stream));
   g.have_colours = true;
