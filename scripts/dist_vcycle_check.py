@@ -39,14 +39,14 @@ mg.vCycle(cycles)
 hist, x = mg.residuals_, mg.grid(-1).values_
 b = capi.partition_bounds(x.size, world)
 own = slice(int(b[rank]), int(b[rank + 1]))
-ok_hist = np.array_equal(hist, ref_hist)
+ok_hist = np.allclose(hist, ref_hist, rtol=1e-12, atol=0)   # the norm is reduced in a different order (per-rank partials + allreduce)
 ok_x = np.array_equal(x[own], ref_x[own])
 halo_ok = np.array_equal(x, ref_x)
 st = mg.comm_stats()
 flags = torch.tensor([int(ok_hist), int(ok_x)], device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("world %d sides %s: history identical %s, owned solution identical %s (rank0 full vector identical %s); partitioned levels %d, %d messages, %.1f MB sent by rank 0; final residual %.3e"
+    print("world %d sides %s: history equal to 1e-12 %s, owned solution identical %s (rank0 full vector identical %s); partitioned levels %d, %d messages, %.1f MB sent by rank 0; final residual %.3e"
           % (world, sides, bool(flags[0].item()), bool(flags[1].item()), halo_ok, st["partitioned_levels"], st["messages"], st["bytes_sent"] / 1e6, hist[-1]))
 dist.barrier()
 dist.destroy_process_group()
