@@ -662,11 +662,12 @@ __global__ void __launch_bounds__(kBlock) k_sor_lex_pipe(HybView A, const unsign
   }
 }
 
-// Chunked variant of the pipelined sweep.  The critical path of the lexicographic DAG runs mostly along
-// CONSECUTIVE rows (scripts/dag_chunks.py: with 16-row chunks ~78 % of its edges stay inside a chunk), and a
-// hand-off through L2 costs ~1.2 us while one through shared memory costs ~0.3 us.  So a CTA of K warps takes a
-// chunk of K consecutive rows (warp w <-> row lo+w): dependencies on rows of the same chunk are polled in shared
-// memory, everything else (earlier chunks of this sweep, the previous sweep) in L2 as before.  CTAs are dealt to
+// Chunked variant of the pipelined sweep (the default).  The critical path of the lexicographic DAG runs mostly along
+// CONSECUTIVE rows (with 32-row chunks ~83 % of its edges stay inside a chunk), and a hand-off through
+// L2 costs ~1.2 us while one through shared memory costs ~0.65 us.  So a CTA of K warps takes a chunk of K consecutive
+// rows (warp w <-> row lo+w): a row waits for the rows of its own chunk on an mbarrier (hardware-suspended, one arrival
+// per producer) and reads their values from shared memory; everything else (earlier chunks of this sweep, the previous
+// sweep) is polled in L2 as before.  CTAs are dealt to
 // sweeps round-robin and walk their chunks in increasing order, so the deadlock-freedom argument of
 // k_sor_lex_pipe carries over unchanged.  Reference-order arithmetic.
 // optional timing trace of one CTA (diagnostics; MMG_LEX_TRACE=1 and mmg_debug_lex_trace())
@@ -680,6 +681,7 @@ __global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsig
   __shared__ double xs_s[K];                 // this chunk's new values
   __shared__ unsigned long long bars[K];     // bars[w]: one arrival per in-chunk dependency of row lo+w
   __shared__ unsigned depmask[K];            // bit j of depmask[w]: row lo+w reads row lo+j (j < w)
+  __shared__ __align__(16) double prod_s[K][T * 32 + 2];   // per warp: its row's products in column order, for the in-order fold
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sweep = 1 + blockIdx.x % iters;
   const int q = blockIdx.x / iters, Q = gridDim.x / iters;
@@ -800,9 +802,30 @@ __global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsig
     LEX_STAMP(4);
     double xi = 0.0;
     if (!aborted) {
-      double s = 0.0;
+      // in-order fold fed from shared memory: every lane writes its products, then the whole warp reads them back with
+      // broadcast 128-bit loads (18 loads for 36 entries instead of 72 shuffles) and runs the serial DSUB chain
 #pragma unroll
-      for (int t = 0; t < T; t++) s = fold_sub32(s, prod[t], m - 1 - t * 32);
+      for (int t = 0; t < T; t++) prod_s[warp][lane + t * 32] = prod[t];
+      __syncwarp();
+      double s = 0.0;
+      const int cnt = m - 1;
+      const double2* p2 = reinterpret_cast<const double2*>(prod_s[warp]);
+#pragma unroll
+      for (int t = 0; t < T; t++) {                 // 32 entries at a time: all 16 loads first, then the chain
+        if (cnt > t * 32) {
+          double2 q[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) q[i] = p2[t * 16 + i];
+#pragma unroll
+          for (int g4 = 0; g4 < 4; g4++) {          // groups of 8 entries; absent entries are 0.0 and s - 0.0 == s
+            if (cnt > t * 32 + g4 * 8) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) { s = __dsub_rn(s, q[g4 * 4 + i].x); s = __dsub_rn(s, q[g4 * 4 + i].y); }
+            }
+          }
+        }
+      }
+      __syncwarp();
       xi = __dadd_rn(s, bi);
       xi = __dmul_rn(xi, wd);
       xi = __dadd_rn(xi, __dmul_rn(1 - omega, __shfl_sync(0xffffffffu, xo, 0)));
@@ -1723,13 +1746,15 @@ static void launch_lex_pipe(Grid& g) {
   if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
   k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
   MMG_CUDA(cudaGetLastError());
-  const int chunk = env_int("MMG_LEX_CHUNK", 0);   // chunked variant (shared-memory hand-offs): opt-in, see DESIGN.md §5
-  if (chunk > 0) {
-    if (chunk == 8) launch_lex_chunk<T, 8>(g, stride);
-    else if (chunk == 32) launch_lex_chunk<T, 32>(g, stride);
-    else launch_lex_chunk<T, 16>(g, stride);
-    MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
-    return;
+  const int chunk = env_int("MMG_LEX_CHUNK", 32);  // rows per CTA chunk of the chunked sweep (0 = warp-per-row pipelined kernel), DESIGN.md §5
+  if constexpr (T <= 4) {
+    if (chunk > 0) {
+      if (chunk == 8) launch_lex_chunk<T, 8>(g, stride);
+      else if (chunk == 32) launch_lex_chunk<T, 32>(g, stride);
+      else launch_lex_chunk<T, 16>(g, stride);
+      MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
+      return;
+    }
   }
   int blocks_per_sm = 0;
   MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_lex_pipe<T>, kBlock, 0));
