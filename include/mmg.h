@@ -116,6 +116,20 @@ int mmg_grid_set_block_size(mmg_grid* g, int rows_per_block);                   
 int mmg_grid_get_block_colouring(mmg_grid* g, int* n_blocks, int* n_colours, int* colour, int cap); /* colour of each block (bit-exact vs oracle) */
 int mmg_grid_get_lex_levels(mmg_grid* g, int* n_levels, int* level);               /* dependency-DAG level of each row, -1 if skipped */
 
+/* ---------------------------------------------------------------- FractionalStepGrid (fractionalStepGrid.hpp:4-30) -------- */
+enum { MMG_FS_U = 0, MMG_FS_V = 1, MMG_FS_U_OLD = 2, MMG_FS_V_OLD = 3, MMG_FS_U_HAT = 4, MMG_FS_V_HAT = 5, MMG_FS_BOTH = -1 };
+int mmg_grid_fs_init(mmg_grid* g, double dt, double mu, double rho);               /* FractionalStepGrid ctor (fractionalStepGrid.cpp:2-17) + dt/mu/rho */
+int mmg_grid_fs_build_operators(mmg_grid* g);                                      /* build_derivX_mat, build_derivY_mat, build_uv_laplace_mat :60-100 */
+int mmg_grid_fs_set_operator_csr(mmg_grid* g, int which, int rows, const int* ptr, const int* idx, const double* val); /* upload path for derivXMat_/derivYMat_/uvLaplaceMat_ */
+int mmg_grid_fs_get_vec(mmg_grid* g, int which, double* out);                      /* u, v, u_old, v_old, u_hat, v_hat (N entries) */
+int mmg_grid_fs_set_vec(mmg_grid* g, int which, const double* in);
+int mmg_grid_fs_scatter(mmg_grid* g, int which, int count, const int* idx, const double* vals); /* the boundary writes of set_uv_bound :41-59 (values evaluated by the caller's libm) */
+int mmg_grid_fs_set_uv_bound(mmg_grid* g);                                         /* set_uv_bound :41-59 (kovasznay), host libm like the reference */
+int mmg_grid_fs_calc_hat(mmg_grid* g, int component);                              /* calc_u_hat (MMG_FS_U) :101-112, calc_v_hat (MMG_FS_V) :113-124, or MMG_FS_BOTH */
+int mmg_grid_fs_set_ppe_source(mmg_grid* g);                                       /* set_ppe_source :125-145 */
+int mmg_grid_fs_correct(mmg_grid* g, int component);                               /* correct_u :146-148, correct_v :149-151, or MMG_FS_BOTH */
+int mmg_grid_fs_residual(mmg_grid* g, double* out);                                /* fs_residual :152-154 */
+
 /* ---------------------------------------------------------------- Multigrid ----------------- */
 int mmg_solver_create(mmg_solver** out, int flavour);                              /* Multigrid::Multigrid / FractionalStepMultigrid */
 int mmg_solver_destroy(mmg_solver* s);                                             /* ~Multigrid (owns its grids) multigrid.cpp:10-16 */

@@ -22,6 +22,7 @@ FLAVOUR_MULTIGRID, FLAVOUR_FRACSTEP = 0, 1
 ARITH_REFERENCE_ORDER, ARITH_FAST = 0, 1
 MAT_LAPLACE, MAT_NEUMANN_COEFFS, MAT_RESTRICT, MAT_PROLONG, MAT_DERIVX, MAT_DERIVY, MAT_UVLAPLACE = range(7)
 T_SOR, T_RESIDUAL, T_RESTRICT, T_PROLONG, T_OTHER, T_COUNT = range(6)
+FS_U, FS_V, FS_U_OLD, FS_V_OLD, FS_U_HAT, FS_V_HAT = range(6)
 
 
 class MmgProps(C.Structure):
@@ -84,6 +85,17 @@ SIGNATURES = {
     "mmg_grid_get_colour_counts": [_vp, C.POINTER(_i), _vp, _i],
     "mmg_grid_set_block_size": [_vp, _i],
     "mmg_grid_get_block_colouring": [_vp, C.POINTER(_i), C.POINTER(_i), _vp, _i],
+    "mmg_grid_fs_init": [_vp, _d, _d, _d],
+    "mmg_grid_fs_build_operators": [_vp],
+    "mmg_grid_fs_set_operator_csr": [_vp, _i, _i, _ip, _ip, _dp],
+    "mmg_grid_fs_get_vec": [_vp, _i, _dp],
+    "mmg_grid_fs_set_vec": [_vp, _i, _dp],
+    "mmg_grid_fs_scatter": [_vp, _i, _i, _ip, _dp],
+    "mmg_grid_fs_set_uv_bound": [_vp],
+    "mmg_grid_fs_calc_hat": [_vp, C.c_int],
+    "mmg_grid_fs_set_ppe_source": [_vp],
+    "mmg_grid_fs_correct": [_vp, C.c_int],
+    "mmg_grid_fs_residual": [_vp, C.POINTER(_d)],
     "mmg_solver_create": [C.POINTER(_vp), _i],
     "mmg_solver_destroy": [_vp],
     "mmg_solver_add_grid": [_vp, _vp],
@@ -277,7 +289,7 @@ class Grid:
     def csr(self, which=MAT_LAPLACE):
         nnz = C.c_int64()
         _ck(self.L, self.L.mmg_grid_csr_nnz(self.h, which, nnz))
-        rows = self.A_size
+        rows = self.getSize() if which in (MAT_DERIVX, MAT_DERIVY, MAT_UVLAPLACE) else self.A_size
         ptr, idx, val = np.empty(rows + 1, np.int32), np.empty(nnz.value, np.int32), np.empty(nnz.value)
         _ck(self.L, self.L.mmg_grid_get_csr(self.h, which, ptr, idx, val))
         return (rows, rows), ptr, idx, val
@@ -356,6 +368,48 @@ class Grid:
         w, nb = np.empty((px.size, n)), np.empty((px.size, n), np.int32)
         _ck(self.L, self.L.mmg_grid_point_interp_weights(self.h, px.size, px, py, polyDeg, w.reshape(-1), nb.reshape(-1)))
         return w, nb
+
+    # ---- FractionalStepGrid (fractionalStepGrid.hpp:4-30)
+    def fs_init(self, dt, mu, rho):
+        _ck(self.L, self.L.mmg_grid_fs_init(self.h, dt, mu, rho))
+
+    def fs_build_operators(self):
+        """build_derivX_mat(); build_derivY_mat(); build_uv_laplace_mat()"""
+        _ck(self.L, self.L.mmg_grid_fs_build_operators(self.h))
+
+    def fs_set_operator_csr(self, which, ptr, idx, val):
+        ptr, idx, val = _i32(ptr), _i32(idx), _f64(val)
+        _ck(self.L, self.L.mmg_grid_fs_set_operator_csr(self.h, which, ptr.size - 1, ptr, idx, val))
+
+    def fs_vec(self, which):
+        out = np.empty(self.getSize())
+        _ck(self.L, self.L.mmg_grid_fs_get_vec(self.h, which, out))
+        return out
+
+    def fs_set_vec(self, which, v):
+        v = _f64(v)
+        assert v.size == self.getSize()
+        _ck(self.L, self.L.mmg_grid_fs_set_vec(self.h, which, v))
+
+    def set_uv_bound(self):
+        """fractionalStepGrid.cpp:41-59 (kovasznay): exact velocities on every boundary node into u, v, u_old, v_old."""
+        _ck(self.L, self.L.mmg_grid_fs_set_uv_bound(self.h))
+
+    def calc_hat(self):
+        """calc_u_hat(); calc_v_hat()"""
+        _ck(self.L, self.L.mmg_grid_fs_calc_hat(self.h, -1))
+
+    def set_ppe_source(self):
+        _ck(self.L, self.L.mmg_grid_fs_set_ppe_source(self.h))
+
+    def correct_uv(self):
+        """correct_u(); correct_v()"""
+        _ck(self.L, self.L.mmg_grid_fs_correct(self.h, -1))
+
+    def fs_residual(self):
+        r = _d()
+        _ck(self.L, self.L.mmg_grid_fs_residual(self.h, r))
+        return r.value
 
     # ---- upload path + artefacts
     def set_laplacian_csr(self, ptr, idx, val, diags=None, nbc=None):

@@ -53,6 +53,9 @@ class HostVector {
   void setZero() { std::fill(h_.begin(), h_.end(), 0.0); device_newer_ = false; host_newer_ = true; }
   const std::vector<double>& host() const { pull(); return h_; }
   HostVector& operator=(const std::vector<double>& v) { h_ = v; device_newer_ = false; host_newer_ = true; return *this; }
+  // *u_old = *u copies the values, never the binding
+  HostVector& operator=(const HostVector& o) { if (this != &o) { if (g_) *this = o.host(); else { h_ = o.host(); } } return *this; }
+  HostVector(const HostVector&) = delete;
   double lpNorm1() const { pull(); double s = 0; for (double t : h_) s += t < 0 ? -t : t; return s; }
 #ifdef MMG_FACADE_HAVE_EIGEN
   operator Eigen::VectorXd() const { pull(); return Eigen::Map<const Eigen::VectorXd>(h_.data(), (Eigen::Index)h_.size()); }
@@ -73,7 +76,7 @@ class HostVector {
   bool host_newer_ = false;
 };
 
-class Multigrid;
+template <class GridT> class BasicMultigrid;
 
 // grid.h:20-79
 class Grid {
@@ -148,8 +151,11 @@ class Grid {
   int getPolyDeg() const { return properties_.polyDeg; }
   mmg_grid* handle() { return h_; }
 
+ protected:
+  void push_all() { sync_flags(); push(); }
+
  private:
-  friend class Multigrid;
+  template <class GridT> friend class BasicMultigrid;
   void sync_flags() { check(mmg_grid_set_implicit(h_, implicitFlag_), "implicitFlag_"); }
   void push() { values_->push(); source_.push(); }
   void refresh() {   // after a reordering the host-side copies of points_/boundaries_ follow the device
@@ -169,22 +175,80 @@ class Grid {
   bool owned_ = true;
 };
 
-// multigrid.h:4-23; FractionalStepMultigrid (FracStepMultigrid.hpp:4-25) is the same class with the twin's flavour
-class Multigrid {
+// fractionalStepGrid.hpp:4-30.  The six velocity vectors live on the device; u, v, ... are HostVector mirrors bound to
+// them, so driver statements like (*grid->u)(i) or grid->u_old = ... keep compiling.  dt / mu / rho are plain members the
+// drivers assign after construction (FractionalStepSim.cpp:26-29); they are pushed with every call that reads them.
+class FractionalStepGrid : public Grid {
  public:
-  std::vector<std::pair<int, Grid*>> grids_;
+  double dt = 0, ppe_conv_res = 0, rho = 1, mu = 1, lambda = 0;
+  std::string flowType = "kovasznay";
+  HostVector u_h_, v_h_, u_old_h_, v_old_h_, u_hat_h_, v_hat_h_;
+  HostVector *u = &u_h_, *v = &v_h_, *u_old = &u_old_h_, *v_old = &v_old_h_, *u_hat = &u_hat_h_, *v_hat = &v_hat_h_;
+
+  FractionalStepGrid(std::vector<Point> points, std::vector<Boundary> boundaries, GridProperties properties, const std::vector<double>& source, int device = 0)
+      : Grid(std::move(points), std::move(boundaries), properties, source, device) {
+    check(mmg_grid_fs_init(handle(), dt, mu, rho), "FractionalStepGrid::FractionalStepGrid");
+    const int n = laplaceMatSize_;
+    u_h_.bind(handle(), n, get<MMG_FS_U>, set<MMG_FS_U>);             v_h_.bind(handle(), n, get<MMG_FS_V>, set<MMG_FS_V>);
+    u_old_h_.bind(handle(), n, get<MMG_FS_U_OLD>, set<MMG_FS_U_OLD>); v_old_h_.bind(handle(), n, get<MMG_FS_V_OLD>, set<MMG_FS_V_OLD>);
+    u_hat_h_.bind(handle(), n, get<MMG_FS_U_HAT>, set<MMG_FS_U_HAT>); v_hat_h_.bind(handle(), n, get<MMG_FS_V_HAT>, set<MMG_FS_V_HAT>);
+  }
+  void set_uv_bound() {
+    if (flowType != "kovasznay") return;          // the reference does nothing for any other flow type (fractionalStepGrid.cpp:45)
+    sync_fs(); check(mmg_grid_fs_set_uv_bound(handle()), "set_uv_bound");
+    u_h_.invalidate(); v_h_.invalidate(); u_old_h_.invalidate(); v_old_h_.invalidate();
+  }
+  // the three builders share one kNN pass on the device; the first call builds all of them
+  void build_derivX_mat() { build_ops(); }
+  void build_derivY_mat() { build_ops(); }
+  void build_uv_laplace_mat() { build_ops(); }
+  void calc_u_hat() { sync_fs(); check(mmg_grid_fs_calc_hat(handle(), MMG_FS_U), "calc_u_hat"); u_hat_h_.invalidate(); }
+  void calc_v_hat() { sync_fs(); check(mmg_grid_fs_calc_hat(handle(), MMG_FS_V), "calc_v_hat"); v_hat_h_.invalidate(); }
+  void set_ppe_source() { sync_fs(); check(mmg_grid_fs_set_ppe_source(handle()), "set_ppe_source"); source_.invalidate(); }
+  void correct_u() { sync_fs(); check(mmg_grid_fs_correct(handle(), MMG_FS_U), "correct_u"); u_h_.invalidate(); }
+  void correct_v() { sync_fs(); check(mmg_grid_fs_correct(handle(), MMG_FS_V), "correct_v"); v_h_.invalidate(); }
+  double fs_residual() {
+    sync_fs();
+    double r = 0;
+    check(mmg_grid_fs_residual(handle(), &r), "fs_residual");
+    return r;
+  }
+
+ private:
+  bool built_ = false;
+  template <int W> static int get(mmg_grid* g, double* out) { return mmg_grid_fs_get_vec(g, W, out); }
+  template <int W> static int set(mmg_grid* g, const double* in) { return mmg_grid_fs_set_vec(g, W, in); }
+  void build_ops() {
+    if (built_) return;
+    sync_fs(); check(mmg_grid_fs_build_operators(handle()), "build_deriv*_mat"); built_ = true;
+  }
+  void sync_fs() {
+    push_all();
+    check(mmg_grid_fs_init(handle(), dt, mu, rho), "dt/mu/rho");
+    u_h_.push(); v_h_.push(); u_old_h_.push(); v_old_h_.push(); u_hat_h_.push(); v_hat_h_.push();
+  }
+};
+
+// multigrid.h:4-23; FractionalStepMultigrid (FracStepMultigrid.hpp:4-25) is the same class over FractionalStepGrid* with
+// the twin's flavour, so both are one template here.
+template <class GridT>
+class BasicMultigrid {
+ public:
+  std::vector<std::pair<int, GridT*>> grids_;
   std::vector<double> residuals_;
 
-  explicit Multigrid(int flavour = MMG_FLAVOUR_MULTIGRID) { check(mmg_solver_create(&h_, flavour), "Multigrid::Multigrid"); }
-  ~Multigrid() {
+  explicit BasicMultigrid(int flavour = MMG_FLAVOUR_MULTIGRID) { check(mmg_solver_create(&h_, flavour), "Multigrid::Multigrid"); }
+  BasicMultigrid(const BasicMultigrid&) = delete;
+  BasicMultigrid& operator=(const BasicMultigrid&) = delete;
+  ~BasicMultigrid() {
     for (auto& g : grids_) delete g.second;      // takes ownership like multigrid.cpp:10-16 (device grids go with the solver)
     mmg_solver_destroy(h_);
   }
-  void addGrid(Grid* grid) {
+  void addGrid(GridT* grid) {
     grid->push();
     check(mmg_solver_add_grid(h_, grid->h_), "Multigrid::addGrid");
     grid->owned_ = false;
-    grids_.push_back(std::pair<int, Grid*>(grid->getSize(), grid));
+    grids_.push_back(std::pair<int, GridT*>(grid->getSize(), grid));
     std::sort(grids_.begin(), grids_.end());     // multigrid.cpp:116-122
   }
   void buildMatrices() {
@@ -214,9 +278,11 @@ class Multigrid {
   mmg_solver* h_ = nullptr;
 };
 
-class FractionalStepMultigrid : public Multigrid {
+typedef BasicMultigrid<Grid> Multigrid;
+
+class FractionalStepMultigrid : public BasicMultigrid<FractionalStepGrid> {
  public:
-  FractionalStepMultigrid() : Multigrid(MMG_FLAVOUR_FRACSTEP) {}
+  FractionalStepMultigrid() : BasicMultigrid<FractionalStepGrid>(MMG_FLAVOUR_FRACSTEP) {}
   void solveLoop() {}   // empty in the reference too (FracStepMultigrid.cpp:113-115)
 };
 

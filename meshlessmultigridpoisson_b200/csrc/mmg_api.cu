@@ -11,6 +11,7 @@ namespace mmg {
 static thread_local std::string g_last_error;
 
 Grid::~Grid() {
+  delete fs;
   asm_release(*this);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -483,6 +484,11 @@ int mmg_grid_get_boundary(mmg_grid* g, int boundary, int* type, int* count, int*
   API_END
 }
 static void grid_csr(Grid& gr, int which, HostCsr& A) {
+  if (which == MMG_MAT_DERIVX || which == MMG_MAT_DERIVY || which == MMG_MAT_UVLAPLACE) {
+    MMG_REQUIRE(gr.fs && gr.fs->have_ops, MMG_ERR_STATE, "the fractional-step operators have not been built or uploaded");
+    hyb_to_csr(which == MMG_MAT_DERIVX ? gr.fs->Dx : which == MMG_MAT_DERIVY ? gr.fs->Dy : gr.fs->Lap, A, gr.stream);
+    return;
+  }
   if (which == MMG_MAT_LAPLACE) {
     MMG_REQUIRE(gr.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
     hyb_to_csr(gr.Lap, A, gr.stream);
@@ -570,6 +576,162 @@ int mmg_grid_get_lex_levels(mmg_grid* g, int* n_levels, int* level) {
   std::vector<int> lv;
   compute_lex_levels(gr, lv, *n_levels);
   std::memcpy(level, lv.data(), sizeof(int) * gr.A);
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------ fractional step
+static void fs_refresh_boundary(Grid& g) {
+  std::vector<int> pts;
+  for (const Boundary& b : g.boundaries) pts.insert(pts.end(), b.pts.begin(), b.pts.end());
+  g.fs->bnd_pts.upload(pts, g.stream);
+  g.fs->nx.upload(g.hnx, g.stream); g.fs->ny.upload(g.hny, g.stream);
+  g.sync();
+}
+int mmg_grid_fs_init(mmg_grid* g, double dt, double mu, double rho) {
+  API_BEGIN
+  NEED(g);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  if (!gr.fs) {
+    gr.fs = new Grid::FracStep();
+    for (int i = 0; i < 6; i++) { gr.fs->vec[i].alloc(gr.n); gr.fs->vec[i].zero(gr.stream); }   // fractionalStepGrid.cpp:5-16
+    gr.fs->t0.alloc(gr.n); gr.fs->t1.alloc(gr.n); gr.fs->t2.alloc(gr.n);
+  }
+  gr.fs->dt = dt; gr.fs->mu = mu; gr.fs->rho = rho;
+  fs_refresh_boundary(gr);
+  API_END
+}
+int mmg_grid_fs_build_operators(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  use_device(G(g).device);
+  asm_build_fs_operators(G(g));
+  fs_refresh_boundary(G(g));
+  API_END
+}
+int mmg_grid_fs_set_operator_csr(mmg_grid* g, int which, int rows, const int* ptr, const int* idx, const double* val) {
+  API_BEGIN
+  NEED(g); NEED(ptr); NEED(idx); NEED(val);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  MMG_REQUIRE(gr.fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  MMG_REQUIRE(which == MMG_MAT_DERIVX || which == MMG_MAT_DERIVY || which == MMG_MAT_UVLAPLACE, MMG_ERR_ARG, "which must be MMG_MAT_DERIVX, _DERIVY or _UVLAPLACE");
+  MMG_REQUIRE(rows == gr.n, MMG_ERR_ARG, "the fractional-step operators are N x N");
+  HostCsr A;
+  A.rows = rows; A.cols = rows;
+  A.ptr.assign(ptr, ptr + rows + 1); A.idx.assign(idx, idx + ptr[rows]); A.val.assign(val, val + ptr[rows]);
+  for (int c : A.idx) MMG_REQUIRE(c >= 0 && c < rows, MMG_ERR_ARG, "column index out of range");
+  HybMatrix& M = which == MMG_MAT_DERIVX ? gr.fs->Dx : which == MMG_MAT_DERIVY ? gr.fs->Dy : gr.fs->Lap;
+  hyb_from_csr(M, A, false, false, gr.stream);
+  gr.fs->have_ops = gr.fs->Dx.rows == gr.n && gr.fs->Dy.rows == gr.n && gr.fs->Lap.rows == gr.n;
+  fs_refresh_boundary(gr);
+  API_END
+}
+static DevBuf<double>& fs_vec(Grid& gr, int which) {
+  MMG_REQUIRE(gr.fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  MMG_REQUIRE(which >= 0 && which < 6, MMG_ERR_ARG, "vector selector must be MMG_FS_U .. MMG_FS_V_HAT");
+  return gr.fs->vec[which];
+}
+int mmg_grid_fs_get_vec(mmg_grid* g, int which, double* out) {
+  API_BEGIN
+  NEED(g); NEED(out);
+  use_device(G(g).device);
+  fs_vec(G(g), which).download(out, G(g).n, G(g).stream);
+  API_END
+}
+int mmg_grid_fs_set_vec(mmg_grid* g, int which, const double* in) {
+  API_BEGIN
+  NEED(g); NEED(in);
+  use_device(G(g).device);
+  MMG_CUDA(cudaMemcpyAsync(fs_vec(G(g), which).p, in, sizeof(double) * G(g).n, cudaMemcpyHostToDevice, G(g).stream));
+  G(g).sync();
+  API_END
+}
+int mmg_grid_fs_scatter(mmg_grid* g, int which, int count, const int* idx, const double* vals) {
+  API_BEGIN
+  NEED(g); NEED(idx); NEED(vals);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  DevBuf<double>& v = fs_vec(gr, which);
+  for (int i = 0; i < count; i++) MMG_REQUIRE(idx[i] >= 0 && idx[i] < gr.n, MMG_ERR_ARG, "scatter index out of range");
+  for (int i = 0; i < count; i++) MMG_CUDA(cudaMemcpyAsync(v.p + idx[i], vals + i, sizeof(double), cudaMemcpyHostToDevice, gr.stream));
+  gr.sync();
+  API_END
+}
+__global__ void k_fs_scatter_uv(int count, const int* __restrict__ idx, const double* __restrict__ uv, const double* __restrict__ vv,
+                                double* u, double* v, double* uo, double* vo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int c = idx[i];
+  u[c] = uv[i]; uo[c] = uv[i];
+  v[c] = vv[i]; vo[c] = vv[i];
+}
+static void fs_scatter_pairs(Grid& gr, const std::vector<int>& idx, const std::vector<double>& uval, const std::vector<double>& vval) {
+  const int count = (int)idx.size();
+  if (count == 0) return;
+  DevBuf<int> di; DevBuf<double> du, dv;
+  di.alloc(count); du.alloc(count); dv.alloc(count);
+  di.upload(idx.data(), count, gr.stream); du.upload(uval.data(), count, gr.stream); dv.upload(vval.data(), count, gr.stream);
+  k_fs_scatter_uv<<<(count + 255) / 256, 256, 0, gr.stream>>>(count, di.p, du.p, dv.p, gr.fs->vec[MMG_FS_U].p, gr.fs->vec[MMG_FS_V].p,
+                                                              gr.fs->vec[MMG_FS_U_OLD].p, gr.fs->vec[MMG_FS_V_OLD].p);
+  MMG_CUDA(cudaGetLastError());
+  gr.sync();
+}
+// fractionalStepGrid.cpp:41-59: the Kovasznay velocities on every boundary node, evaluated on the host with the same libm
+// calls the reference makes (std::exp / std::cos / std::sin on doubles), written into u, v, u_old and v_old.
+int mmg_grid_fs_set_uv_bound(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  Grid& gr = G(g);
+  MMG_REQUIRE(gr.fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  use_device(gr.device);
+  const double pi = 3.141592653589793238462643383279502884;
+  const double re = gr.fs->rho / gr.fs->mu;
+  const double lambda = 0.5 * re - std::sqrt(0.25 * re * re + 4 * pi * pi);
+  std::vector<int> idx;
+  std::vector<double> uval, vval;
+  for (const Boundary& b : gr.boundaries)
+    for (int c : b.pts) {
+      const double x = gr.hx[c], y = gr.hy[c];
+      idx.push_back(c);
+      uval.push_back(1 - std::exp(lambda * x) * std::cos(2 * pi * y));
+      vval.push_back(lambda / (2 * pi) * std::exp(lambda * x) * std::sin(2 * pi * y));
+    }
+  fs_scatter_pairs(gr, idx, uval, vval);
+  API_END
+}
+int mmg_grid_fs_calc_hat(mmg_grid* g, int component) {
+  API_BEGIN
+  NEED(g);
+  MMG_REQUIRE(G(g).fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  use_device(G(g).device);
+  MMG_REQUIRE(component == MMG_FS_BOTH || component == MMG_FS_U || component == MMG_FS_V, MMG_ERR_ARG, "component must be MMG_FS_U, MMG_FS_V or MMG_FS_BOTH");
+  fs_calc_hat(G(g), component);
+  API_END
+}
+int mmg_grid_fs_set_ppe_source(mmg_grid* g) {
+  API_BEGIN
+  NEED(g);
+  MMG_REQUIRE(G(g).fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  use_device(G(g).device);
+  fs_set_ppe_source(G(g));
+  API_END
+}
+int mmg_grid_fs_correct(mmg_grid* g, int component) {
+  API_BEGIN
+  NEED(g);
+  MMG_REQUIRE(G(g).fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  use_device(G(g).device);
+  MMG_REQUIRE(component == MMG_FS_BOTH || component == MMG_FS_U || component == MMG_FS_V, MMG_ERR_ARG, "component must be MMG_FS_U, MMG_FS_V or MMG_FS_BOTH");
+  fs_correct(G(g), component);
+  API_END
+}
+int mmg_grid_fs_residual(mmg_grid* g, double* out) {
+  API_BEGIN
+  NEED(g); NEED(out);
+  MMG_REQUIRE(G(g).fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  use_device(G(g).device);
+  *out = fs_residual(G(g));
   API_END
 }
 

@@ -680,6 +680,39 @@ void asm_build_interp(Grid& base, Grid& target, int polyDeg, HybMatrix& M) {
   base.sync();
 }
 
+// FractionalStepGrid::build_derivX_mat / build_derivY_mat / build_uv_laplace_mat (fractionalStepGrid.cpp:60-100): N x N, one
+// stencil row per node (no boundary-condition rows), the same neighbour lists for the three operators
+void asm_build_fs_operators(Grid& g) {
+  MMG_REQUIRE(g.fs != nullptr, MMG_ERR_STATE, "mmg_grid_fs_init has not been called");
+  AsmState& st = state(g);
+  if (!st.cells_valid) build_cells(g);
+  MMG_REQUIRE(g.props.stencilSize == stencil_of(g.props.polyDeg), MMG_ERR_ARG, "stencilSize must equal (int)(2.5*(p+1)(p+2)/2)");
+  const int N = g.n, n = g.props.stencilSize;
+  DevBuf<int> dnb, dids, dqf;
+  dnb.alloc((size_t)N * n);
+  std::vector<int> qf(N), ids(N);
+  for (int i = 0; i < N; i++) { qf[i] = g.bcflags[i] != 0; ids[i] = i; }
+  dqf.upload(qf, g.stream); dids.upload(ids, g.stream);
+  knn_device(g, N, g.px.p, g.py.p, dqf.p, g.neumann ? 1 : 0, n, dnb.p);
+  HybMatrix* mats[3] = {&g.fs->Dx, &g.fs->Dy, &g.fs->Lap};
+  const int modes[3] = {W_DX, W_DY, W_LAPLACE};
+  for (int o = 0; o < 3; o++) {
+    HybMatrix& M = *mats[o];
+    M = HybMatrix();
+    M.rows = N; M.cols = N; M.W = n; M.diag_first = false; M.nnz = (int64_t)N * n;
+    M.chunk_bytes = ((size_t)n * 12 + 31) / 32 * 32;
+    M.chunks.alloc((size_t)N * M.chunk_bytes);
+    M.len.alloc(N);
+    WeightJob J{};
+    J.px = g.px.p; J.py = g.py.p; J.nb = dnb.p; J.ids = dids.p;
+    J.systems = N; J.n = n; J.m = poly_terms(g.props.polyDeg); J.S = J.n + J.m; J.polyDeg = g.props.polyDeg; J.mode = modes[o];
+    J.chunks = M.chunks.p; J.chunk_bytes = M.chunk_bytes; J.W = n; J.len = M.len.p; J.diag_first = 0;
+    launch_weights(g, J);
+  }
+  g.sync();
+  g.fs->have_ops = true;
+}
+
 // Grid::build_deriv_normal_bound grid.cpp:520-548
 void asm_build_deriv_normal_bound(Grid& g) {
   AsmState& st = state(g);

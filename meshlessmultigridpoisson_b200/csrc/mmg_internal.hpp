@@ -183,6 +183,17 @@ struct Grid {
   int n_blk_colours = 0;
   std::vector<int> blk_colour, blk_phase_ptr;
   DevBuf<int> blk_phase_blocks;          // block ids grouped by colour
+  // FractionalStepGrid state (fractionalStepGrid.hpp:4-30): created by mmg_grid_fs_init
+  struct FracStep {
+    double dt = 0, mu = 1, rho = 1;
+    DevBuf<double> vec[6];               // u, v, u_old, v_old, u_hat, v_hat (N entries each)
+    DevBuf<double> t0, t1, t2;           // SpMV scratch
+    HybMatrix Dx, Dy, Lap;               // derivXMat_, derivYMat_, uvLaplaceMat_
+    bool have_ops = false;
+    DevBuf<int> bnd_pts;                 // every boundary node, boundary-list order (set_ppe_source visits all boundaries)
+    DevBuf<double> nx, ny;               // normalVecs_
+  };
+  FracStep* fs = nullptr;
   // per-level assembly state (device kNN lists etc.) lives in assembly.cu
   void* asm_state = nullptr;
 
@@ -254,6 +265,12 @@ void asm_build_laplacian(Grid& g);
 void asm_weights(Grid& g, int which, int m, const int* ids, double* w, int* nb);
 void asm_point_interp_weights(Grid& g, int m, const double* px, const double* py, int polyDeg, double* w, int* nb);
 void asm_build_interp(Grid& base, Grid& target, int polyDeg, HybMatrix& out);
+void asm_build_fs_operators(Grid& g);
+// fractional-step explicit operators (kernels.cu)
+void fs_calc_hat(Grid& g, int component);   // MMG_FS_U, MMG_FS_V or MMG_FS_BOTH
+void fs_set_ppe_source(Grid& g);
+void fs_correct(Grid& g, int component);
+double fs_residual(Grid& g);
 
 // ---- timers ---------------------------------------------------------------------------------------
 struct TimedScope {

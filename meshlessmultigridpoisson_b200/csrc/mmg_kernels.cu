@@ -2035,6 +2035,107 @@ void debug_lex_trace(long long* out, int n) {
 }
 
 // ================================================================================================
+// Fractional-step explicit operators (fractionalStepGrid.cpp:101-154)
+// ================================================================================================
+namespace {
+// u_hat = u + dt*(-(u*u_x + v*u_y) + mu/rho*del2_u)   (fractionalStepGrid.cpp:109, 121)
+__global__ void k_fs_hat(int n, const double* __restrict__ w, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ wx,
+                         const double* __restrict__ wy, const double* __restrict__ lap, double dt, double mu_over_rho, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = w[i] + dt * (-(u[i] * wx[i] + v[i] * wy[i]) + mu_over_rho * lap[i]);
+}
+// source_.head(N) = rho/dt * (Dx u_hat + Dy v_hat)   (:127)
+__global__ void k_fs_ppe_interior(int n, const double* __restrict__ a, const double* __restrict__ b, double rho_over_dt, double* __restrict__ src) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) src[i] = rho_over_dt * (a[i] + b[i]);
+}
+// boundary nodes: source_ = nx*dpdx + ny*dpdy, dpdx = -rho/dt*(u - u_hat)   (:132-143)
+__global__ void k_fs_ppe_boundary(int count, const int* __restrict__ pts, const double* __restrict__ u, const double* __restrict__ v,
+                                  const double* __restrict__ uh, const double* __restrict__ vh, const double* __restrict__ nx,
+                                  const double* __restrict__ ny, double neg_rho_over_dt, double* src) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const int c = pts[j];
+  const double dpdx = neg_rho_over_dt * (u[c] - uh[c]);
+  const double dpdy = neg_rho_over_dt * (v[c] - vh[c]);
+  src[c] = nx[c] * dpdx + ny[c] * dpdy;
+}
+// u = u_hat - dt/rho * (Dx p)   (:147, 150)
+__global__ void k_fs_correct(int n, const double* __restrict__ hat, const double* __restrict__ grad, double dt_over_rho, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hat[i] - dt_over_rho * grad[i];
+}
+__global__ void __launch_bounds__(kBlock) k_fs_absdiff(int n, const double* __restrict__ a, const double* __restrict__ b, double* partial) {
+  double s = 0.0, dummy = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += fabs(a[i] - b[i]);
+  block_sum2(s, dummy);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+void fs_spmv(Grid& g, const HybMatrix& M, const double* x, double* y) {
+  launch_spmv(M, x, nullptr, y, nullptr, OP_SPMV, 0, 0, nullptr, nullptr, g.device, g.stream, g.exact);
+}
+}  // namespace
+
+void fs_calc_hat(Grid& g, int component) {
+  Grid::FracStep& F = *g.fs;
+  MMG_REQUIRE(F.have_ops, MMG_ERR_STATE, "the fractional-step operators have not been built or uploaded");
+  const int N = g.n, nb = (N + kBlock - 1) / kBlock;
+  TimedScope ts(g, MMG_T_OTHER, 6 * F.Dx.matrix_bytes() + (int64_t)N * 8 * 14, 8);
+  for (int w = 0; w < 2; w++) {   // w = 0: u_hat from u; w = 1: v_hat from v
+    if (component != MMG_FS_BOTH && component != w) continue;
+    const double* field = F.vec[w].p;
+    fs_spmv(g, F.Dx, field, F.t0.p);
+    fs_spmv(g, F.Dy, field, F.t1.p);
+    fs_spmv(g, F.Lap, field, F.t2.p);
+    k_fs_hat<<<nb, kBlock, 0, g.stream>>>(N, field, F.vec[0].p, F.vec[1].p, F.t0.p, F.t1.p, F.t2.p, F.dt, F.mu / F.rho, F.vec[4 + w].p);
+  }
+  MMG_CUDA(cudaGetLastError());
+}
+
+void fs_set_ppe_source(Grid& g) {
+  Grid::FracStep& F = *g.fs;
+  MMG_REQUIRE(F.have_ops, MMG_ERR_STATE, "the fractional-step operators have not been built or uploaded");
+  const int N = g.n, nb = (N + kBlock - 1) / kBlock;
+  TimedScope ts(g, MMG_T_OTHER, 2 * F.Dx.matrix_bytes() + (int64_t)N * 8 * 6, 4);
+  fs_spmv(g, F.Dx, F.vec[4].p, F.t0.p);
+  fs_spmv(g, F.Dy, F.vec[5].p, F.t1.p);
+  k_fs_ppe_interior<<<nb, kBlock, 0, g.stream>>>(N, F.t0.p, F.t1.p, F.rho / F.dt, g.b.p);
+  const int m = (int)F.bnd_pts.n;
+  if (m) k_fs_ppe_boundary<<<(m + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(m, F.bnd_pts.p, F.vec[0].p, F.vec[1].p, F.vec[4].p, F.vec[5].p, F.nx.p, F.ny.p,
+                                                                                -F.rho / F.dt, g.b.p);
+  MMG_CUDA(cudaGetLastError());
+}
+
+void fs_correct(Grid& g, int component) {
+  Grid::FracStep& F = *g.fs;
+  MMG_REQUIRE(F.have_ops, MMG_ERR_STATE, "the fractional-step operators have not been built or uploaded");
+  const int N = g.n, nb = (N + kBlock - 1) / kBlock;
+  TimedScope ts(g, MMG_T_OTHER, 2 * F.Dx.matrix_bytes() + (int64_t)N * 8 * 6, 4);
+  if (component == MMG_FS_BOTH || component == MMG_FS_U) {
+    fs_spmv(g, F.Dx, g.x.p, F.t0.p);      // values_->head(N): the operators have N columns
+    k_fs_correct<<<nb, kBlock, 0, g.stream>>>(N, F.vec[4].p, F.t0.p, F.dt / F.rho, F.vec[0].p);
+  }
+  if (component == MMG_FS_BOTH || component == MMG_FS_V) {
+    fs_spmv(g, F.Dy, g.x.p, F.t0.p);
+    k_fs_correct<<<nb, kBlock, 0, g.stream>>>(N, F.vec[5].p, F.t0.p, F.dt / F.rho, F.vec[1].p);
+  }
+  MMG_CUDA(cudaGetLastError());
+}
+
+double fs_residual(Grid& g) {   // (*u - *u_hat).lpNorm<1>() / N   (:152-154)
+  Grid::FracStep& F = *g.fs;
+  const int blocks = 256;
+  ensure_partials(g, blocks);
+  k_fs_absdiff<<<blocks, kBlock, 0, g.stream>>>(g.n, F.vec[0].p, F.vec[4].p, g.partials.p);
+  MMG_CUDA(cudaGetLastError());
+  std::vector<double> h(blocks);
+  g.partials.download(h.data(), blocks, g.stream);
+  double s = 0;
+  for (double t : h) s += t;
+  return s / g.n;
+}
+
+// ================================================================================================
 // Multi-GPU: row-block partition of the large levels, halo exchange of contiguous ranges
 // ================================================================================================
 namespace {

@@ -81,3 +81,44 @@ def make_hierarchy(sizes, kind="dirichlet", fine_poly=4, coarse_poly=3, seed0=10
         mg.addGrid(make_grid(kind, x, y, fine_poly if last else coarse_poly, fine=last, device=device, **kw))
     mg.buildMatrices()
     return mg
+
+
+def make_ppe_grid(x, y, poly_deg, dt, mu, rho, fine=True, device=0, **props):
+    """genFractionalStepGrid (FractionalStepSim.cpp:3-49): pressure-Poisson level of the Kovasznay fractional-step driver —
+    all-Neumann square, zero source, boundary values 0.5*exp(2*lambda*x), plus the three explicit operators."""
+    import math
+
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    p = grid_props(poly_deg, **props)
+    re = rho / mu
+    lam = 0.5 * re - math.sqrt(0.25 * re * re + 4 * math.pi * math.pi)
+    pts = np.nonzero((x == 0) | (x == 1) | (y == 0) | (y == 1))[0].astype(np.int32)
+    vals = np.array([0.5 * math.exp(2 * lam * x[i]) for i in pts])
+    g = capi.Grid(x, y, [capi.Boundary(pts, vals, type=capi.BC_NEUMANN)], p, np.zeros(x.size + 1), device=device)
+    g.fs_init(dt, mu, rho)
+    g.set_implicitFlag(True)
+    g.setBCFlag(0, "neumann", vals)
+    g.build_normal_vecs("square")
+    g.rcm_order_points()
+    g.build_deriv_normal_bound()
+    g.build_laplacian()
+    g.modify_coeff_neumann("fine" if fine else "coarse")
+    g.fs_build_operators()
+    g.push_inhomog_to_rhs()
+    return g
+
+
+def fracstep_time_step(mg, tol, max_cycles=200):
+    """One pass of the loop body of run_fracstep_param (FractionalStepSim.cpp:130-147).  Returns (V-cycles used, fs_residual)."""
+    fine = mg.grid(-1)
+    fine.fs_set_vec(capi.FS_U_OLD, fine.fs_vec(capi.FS_U))
+    fine.fs_set_vec(capi.FS_V_OLD, fine.fs_vec(capi.FS_V))
+    fine.set_uv_bound()
+    fine.calc_hat()
+    fine.set_ppe_source()
+    fine.push_inhomog_to_rhs()
+    n, _ = mg.solve(tol, max_cycles, extra_bound_eval=True)     # while (mg.residual() >= tol) { mg.vCycle(); finestGrid->bound_eval_neumann(); }
+    fine.correct_uv()
+    fine.set_uv_bound()
+    return n, fine.fs_residual()

@@ -13,7 +13,7 @@ mg.vCycle(2)
 ms = mg.time_vcycles(cycles) / cycles
 mg.enable_timers(True); mg.reset_timers(); mg.vCycle(cycles)
 out = []
-for l in (len(sides) - 1, len(sides) - 2):
+for l in range(len(sides) - 1, -1, -1):
     t = mg.timers(l)
-    out.append("L%d " % l + " ".join("%s %.0fGB/s(%.2fms)" % (k, v["bytes"] / max(v["ms"], 1e-9) / 1e6, v["ms"] / cycles) for k, v in t.items() if v["ms"] > 0))
+    out.append("L%d(%d) " % (l, sides[l] ** 2) + " ".join("%s %.0fGB/s(%.2fms)" % (k, v["bytes"] / max(v["ms"], 1e-9) / 1e6, v["ms"] / cycles) for k, v in t.items() if v["ms"] > 0))
 print("side %d poly %d env %s: %.2f ms/cycle | %s" % (side, poly, {k: v for k, v in os.environ.items() if k.startswith("MMG_")}, ms, " | ".join(out)))

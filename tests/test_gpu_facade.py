@@ -28,3 +28,33 @@ def test_cpp_driver_matches_python_driver_bit_for_bit(libmmg, tmp_path):
     mg.vCycle(12)
     assert np.array_equal(hist, mg.residuals_)          # same library, same device-built operators: identical
     assert hist[-1] < 2e-3 * hist[0] and err < 1e-3
+
+
+def test_cpp_fracstep_driver_matches_python_driver_bit_for_bit(libmmg, tmp_path):
+    """run_fracstep.cpp keeps the statements of run_fracstep_param (FractionalStepSim.cpp:114-148) over the facade's
+    FractionalStepGrid / FractionalStepMultigrid; the Python driver makes the same C-ABI calls."""
+    from meshlessmultigridpoisson_b200 import capi
+    from meshlessmultigridpoisson_b200.problems import fracstep_time_step, make_ppe_grid
+
+    cpp = os.path.join(ROOT, "meshlessmultigridpoisson_b200", "cpp")
+    subprocess.check_call(["make", "-s", "-C", cpp])
+    sizes, files, clouds = [13, 25, 50], [], []
+    for l, s in enumerate(sizes):
+        x, y = jittered_square(s, seed=1000 + l)
+        fn = str(tmp_path / ("l%d.msh" % l))
+        write_msh_nodes(fn, x, y)
+        files.append(fn)
+        clouds.append((x, y))
+    out = subprocess.check_output([os.path.join(cpp, "run_fracstep"), "3", "1e-6", "3", *files], text=True, env=dict(os.environ, MMG_FS_MAX_CYCLES="200")).split("\n")
+    deltas = [float(t.split()[0]) for t in out[:3]]
+    cycles = [int(t.split()[1]) for t in out[:3]]
+    mg = capi.FractionalStepMultigrid()
+    for l, (x, y) in enumerate(clouds):
+        mg.addGrid(make_ppe_grid(x, y, 3, 2e-4, 0.025, 1.0, fine=(l == len(sizes) - 1)))
+    mg.buildMatrices()
+    old = 1000.0
+    for k in range(3):
+        n, r = fracstep_time_step(mg, 1e-6, 200)
+        assert n == cycles[k] and abs(r - old) == deltas[k]
+        old = r
+    assert 0 < cycles[0] < 200 and float(out[3].split()[1]) < 0.5
