@@ -177,6 +177,8 @@ struct Grid {
   DevBuf<int> colour_ptr_dev;            // colour_ptr on the device (persistent multicolour kernel)
   std::vector<int> colour_host;          // per-row colour (-1 skipped)
   std::vector<int> colour_rows_host;     // host copy of colour_rows (multi-GPU sub-ranges)
+  bool mc_packed = false;
+  DevBuf<unsigned char> mc_chunks;       // colour-major packed copy of Lap.chunks (Morton order inside a colour), fast multicolour sweep
   // block-lexicographic schedule
   int block_size = 4096;
   bool have_blocks = false;
@@ -253,6 +255,7 @@ void op_restrict(Grid& fine, Grid& coarse, const HybMatrix& R, const double* fin
 void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P);
 void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class);
 void build_colouring(Grid& g);
+void ensure_mc_pack(Grid& g);
 void build_block_colouring(Grid& g);
 void compute_lex_levels(Grid& g, std::vector<int>& level, int& n_levels);
 

@@ -1355,6 +1355,100 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_all(HybView A, const int* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Colour-major packed copy of the operator (fourth generation of the multicolour sweep).
+// ncu without cache flushing (profiles/r01_steady_state_4M.txt) showed the per-colour phases of k_sor_mc_all at
+// 46 % of DRAM peak but 72 % of the L2 sector-read cap: a colour's rows are every ~15th row of the matrix, so
+// (a) the 448-byte row chunks are isolated DRAM bursts, (b) rows_list -> len -> chunk -> gather is a four-deep
+// chain of dependent loads, and (c) a CTA's 32 rows lie on a thin arc of one BFS ring, so hardly any gathered sector
+// of x is shared between its warps (37 L2 sectors per row).  The packed copy stores the chunks of every colour
+// contiguously, in Morton order of the node coordinates inside a colour: a phase streams one contiguous range, a
+// CTA tile is a compact 2-D patch whose neighbourhoods overlap in L1, the diagonal slot carries the row index
+// (slot 0's column IS the row, diag_first), and padded slots are (0.0, own row), so neither the row list nor the
+// length array is read.  Rows of one colour are independent, so their order does not change any result.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_chunks(const unsigned char* __restrict__ src, size_t chunk_bytes, const int* __restrict__ rows, int count,
+                              unsigned char* __restrict__ dst) {
+  const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)rows[w] * chunk_bytes);
+  uint4* d = reinterpret_cast<uint4*>(dst + (size_t)w * chunk_bytes);
+  for (int k = lane; k < (int)(chunk_bytes / 16); k += 32) d[k] = s[k];
+}
+
+template <int LPR, int ITER, int ROWS>
+__device__ __forceinline__ void mc_phase_packed(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W, int count,
+                                                const double* __restrict__ b, double* x, double omega) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  constexpr int TR = (kBlock / 32) * GPW * ROWS;
+  const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
+  const int ntiles = (count + TR - 1) / TR;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    double v[ROWS][ITER], xx[ROWS][ITER], bi[ROWS], acc[ROWS];
+    int c[ROWS][ITER];
+    bool valid[ROWS];
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      const int i = tile * TR + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
+      valid[h] = i < count;
+      const double* pv = reinterpret_cast<const double*>(chunks + (size_t)(valid[h] ? i : 0) * chunk_bytes);
+      const int* pc = reinterpret_cast<const int*>(pv + W);
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        const int k = gl + t * LPR;
+        const bool ok = valid[h] && k < W;
+        v[h][t] = ok ? ldg_stream_f64(pv + k, stream) : 0.0;
+        c[h][t] = ok ? ldg_stream_s32(pc + k, stream) : -1;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++)
+#pragma unroll
+      for (int t = 0; t < ITER; t++) xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && valid[h]) ? b[c[h][0]] : 0.0;   // slot 0 is the diagonal: its column is the row
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      double a = 0.0;
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        if (t == 0 && gl == 0) continue;
+        a = __dsub_rn(a, __dmul_rn(v[h][t], xx[h][t]));
+      }
+      acc[h] = a;
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+    if (gl == 0) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) {
+        if (valid[h]) {
+          double xi = __dadd_rn(acc[h], bi[h]);
+          xi = __dmul_rn(xi, omega / v[h][0]);
+          xi = __dadd_rn(xi, __dmul_rn(1 - omega, xx[h][0]));     // xx[h][0] on lane 0 is x[row] before the update
+          x[c[h][0]] = xi;
+        }
+      }
+    }
+  }
+}
+
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kBlock) k_sor_mc_packed(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,
+                                                          const int* __restrict__ colour_ptr, int ncolours, int iters, const double* __restrict__ b,
+                                                          double* x, double omega) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  for (int it = 0; it < iters; it++)
+    for (int c = 0; c < ncolours; c++) {
+      const int first = colour_ptr[c], count = colour_ptr[c + 1] - first;
+      mc_phase_packed<LPR, ITER, ROWS>(chunks + (size_t)first * chunk_bytes, chunk_bytes, W, count, b, x, omega);
+      grid.sync();
+    }
+}
+
 __global__ void k_scatter(const int* __restrict__ idx, const double* __restrict__ vals, int count, double* dst, int use_zero) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) dst[idx[i]] = use_zero ? 0.0 : vals[i];
@@ -1985,6 +2079,37 @@ void op_sor(Grid& g, int smoother) {
     MMG_REQUIRE(!g.neumann, MMG_ERR_STATE, "the block-lexicographic smoother is implemented for grids without Neumann boundaries");
     if (!g.have_blocks) build_block_colouring(g);
   }
+  if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && !g.neumann && L.n_ovf == 0 && L.diag_first && g.props.iters >= 1 &&
+      (int)g.hx.size() == g.n && env_int("MMG_MC_PACKED", 1) && !env_int("MMG_MC_PER_COLOUR", 0)) {
+    ensure_mc_pack(g);
+    bool done = false;
+    {
+      TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
+      const int rows_pref = env_int("MMG_MC_ROWS", 2);
+      done = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+        constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+        void* kern = rows_pref >= 4 ? (void*)k_sor_mc_packed<LPR, ITER, 4> : rows_pref == 1 ? (void*)k_sor_mc_packed<LPR, ITER, 1> : (void*)k_sor_mc_packed<LPR, ITER, 2>;
+        const int rows_used = rows_pref >= 4 ? 4 : rows_pref == 1 ? 1 : 2;
+        int blocks_per_sm = 0;
+        MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
+        const int sms = sm_count_of(g.device);
+        int maxcount = 0;
+        for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.colour_ptr[c + 1] - g.colour_ptr[c]);
+        int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, rows_used));
+        const unsigned char* chunks = g.mc_chunks.p;
+        size_t cb = L.chunk_bytes;
+        int W = L.W;
+        const int* cp = g.colour_ptr_dev.p;
+        int nc = g.n_colours, iters = g.props.iters;
+        const double* b = g.b.p;
+        double* x = g.x.p;
+        double omega = g.props.omega;
+        void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega};
+        MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+      });
+    }
+    if (done) return;
+  }
   if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && !g.neumann && L.n_ovf == 0 && g.props.iters >= 1 && !env_int("MMG_MC_PER_COLOUR", 0)) {
     bool done = false;
     {
@@ -2351,6 +2476,49 @@ void build_colouring(Grid& g) {
   g.colour_ptr_dev.upload(g.colour_ptr, g.stream);
   MMG_CUDA(cudaStreamSynchronize(g.stream));
   g.have_colours = true;
+  g.mc_packed = false;
+  g.mc_chunks.release();
+}
+
+// Colour-major packed copy of laplaceMat_ for k_sor_mc_packed: the rows of every colour in Morton (Z-curve) order of
+// their node coordinates, so that consecutive rows of a colour form compact 2-D patches.
+void ensure_mc_pack(Grid& g) {
+  if (g.mc_packed) return;
+  MMG_REQUIRE(g.have_colours, MMG_ERR_STATE, "ensure_mc_pack: colouring missing");
+  const int total = g.colour_ptr[g.n_colours];
+  std::vector<int> rows(g.colour_rows_host);
+  if (env_int("MMG_MC_ORDER", 1) == 1 && total > 0) {
+    double x0 = g.hx[0], x1 = g.hx[0], y0 = g.hy[0], y1 = g.hy[0];
+    for (int i = 0; i < g.n; i++) { x0 = std::min(x0, g.hx[i]); x1 = std::max(x1, g.hx[i]); y0 = std::min(y0, g.hy[i]); y1 = std::max(y1, g.hy[i]); }
+    const double sx = x1 > x0 ? 65535.0 / (x1 - x0) : 0.0, sy = y1 > y0 ? 65535.0 / (y1 - y0) : 0.0;
+    auto spread = [](uint32_t v) {
+      v &= 0xFFFFu;
+      v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+      return v;
+    };
+    std::vector<std::pair<uint32_t, int>> keyed;
+    for (int c = 0; c < g.n_colours; c++) {
+      const int a = g.colour_ptr[c], e = g.colour_ptr[c + 1];
+      keyed.clear();
+      for (int k = a; k < e; k++) {
+        const int r = rows[k];
+        const uint32_t qx = (uint32_t)((g.hx[r] - x0) * sx), qy = (uint32_t)((g.hy[r] - y0) * sy);
+        keyed.push_back({spread(qx) | (spread(qy) << 1), r});
+      }
+      std::sort(keyed.begin(), keyed.end());
+      for (int k = a; k < e; k++) rows[k] = keyed[k - a].second;
+    }
+  }
+  DevBuf<int> drows;
+  drows.upload(rows, g.stream);
+  g.mc_chunks.alloc((size_t)total * g.Lap.chunk_bytes);
+  if (total > 0) {
+    const long long threads = (long long)total * 32;
+    k_pack_chunks<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, g.stream>>>(g.Lap.chunks.p, g.Lap.chunk_bytes, drows.p, total, g.mc_chunks.p);
+    MMG_CUDA(cudaGetLastError());
+  }
+  MMG_CUDA(cudaStreamSynchronize(g.stream));
+  g.mc_packed = true;
 }
 
 void compute_lex_levels(Grid& g, std::vector<int>& level, int& n_levels) {

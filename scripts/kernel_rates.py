@@ -16,4 +16,9 @@ out = []
 for l in range(len(sides) - 1, -1, -1):
     t = mg.timers(l)
     out.append("L%d(%d) " % (l, sides[l] ** 2) + " ".join("%s %.0fGB/s(%.2fms)" % (k, v["bytes"] / max(v["ms"], 1e-9) / 1e6, v["ms"] / cycles) for k, v in t.items() if v["ms"] > 0))
+try:
+    cc = mg.grid(-1).colour_counts()
+    out.append("finest colours %d sizes max %d min %d" % (len(cc), max(cc), min(cc)))
+except Exception as e:
+    out.append("colour counts unavailable: %s" % e)
 print("side %d poly %d env %s: %.2f ms/cycle | %s" % (side, poly, {k: v for k, v in os.environ.items() if k.startswith("MMG_")}, ms, " | ".join(out)))
