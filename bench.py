@@ -36,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TOL = 1e-8
+NCU_TRAFFIC_FINEST_SOR_LAUNCH = 9192000000 + 49000000   # bytes, see profiles/ (refreshed with every kernel change)
 
 
 def level_sides(side, levels=None):
@@ -256,16 +257,15 @@ def main():
     shares = {k: round(v["ms"] / max(1e-9, sum(x["ms"] for x in tm_all.values())), 4) for k, v in tm_all.items()}
     traffic, per_launch = None, None
     if fast:
-        from meshlessmultigridpoisson_b200.problems import stencil_size
-        counts = fine.colour_counts()
-        per_launch = int(counts.max()) * (12 * stencil_size(args.fine_poly) + 28)     # largest colour phase = one launch
-        if args.side == 2000 and args.fine_poly == 4:
-            # dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full (profiles/r01_sor_mc2_4M_ncu.txt)
-            traffic = 208287488 + 5096448
+        per_launch = sor["bytes"] // max(1, sor["launches"])          # one launch = all nu sweeps of one smoothing call on the finest level
+        if args.side == 2000 and args.fine_poly == 4 and world == 1:
+            # dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full (profiles/r01_sor_mc_packed_4M_ncu.txt)
+            traffic = NCU_TRAFFIC_FINEST_SOR_LAUNCH
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_sor_mc2 (finest level, one launch per colour; achieved = bytes of all colour launches / their CUDA-event time)"
-                if fast else "k_sor_lex_pipe (finest level)",
-                "peak_source": peak_src, "algorithmic_bytes_largest_launch": per_launch, "bytes_per_sweep": sor["bytes"] // max(1, 2 * 5 * args.steps),
+                "kernel": "k_sor_mc_packed (finest level: all colours of all nu sweeps in one cooperative launch over the colour-major packed operator; "
+                          "achieved = algorithmic bytes of those launches / their CUDA-event time)"
+                if fast else "k_sor_lex_chunk (finest level)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch, "bytes_per_sweep": sor["bytes"] // max(1, 2 * 5 * args.steps),
                 "sor_share_of_step": shares.get("sor"), "class_shares": shares,
                 "whole_cycle_GBps": algorithmic_bytes_per_cycle(sides, args.fine_poly) / (ms_per_step * 1e-3) / 1e9}
 

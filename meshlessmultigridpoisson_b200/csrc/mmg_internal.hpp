@@ -179,6 +179,10 @@ struct Grid {
   std::vector<int> colour_rows_host;     // host copy of colour_rows (multi-GPU sub-ranges)
   bool mc_packed = false;
   DevBuf<unsigned char> mc_chunks;       // colour-major packed copy of Lap.chunks (Morton order inside a colour), fast multicolour sweep
+  int mc_regions = 0;                    // > 0: mc_chunks is region-major (k_sor_mc_regions), one region per co-resident CTA
+  DevBuf<int> mc_blk_ptr, mc_nbr_ptr, mc_nbr;   // (region, colour) block offsets; adjacency lists of the regions
+  DevBuf<unsigned> mc_done;              // finished phases per region, monotone across launches
+  unsigned mc_epoch = 0;
   // block-lexicographic schedule
   int block_size = 4096;
   bool have_blocks = false;

@@ -1449,6 +1449,207 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_packed(const unsigned char* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small levels.  Below ~10^4 rows a colour phase is a handful of rows per SM and the cooperative kernel is pure latency:
+// ~1.7 us per phase (grid barrier + an L2 round trip each for chunk, gather and store), 160-220 phases per call, 0.4 ms
+// per level and cycle -- the four coarsest levels cost as much as the whole 1M-row level.  Here ONE CTA of 1024 threads
+// keeps values_ and source_ in shared memory for the whole call, reads the (L2-resident) packed operator with the
+// chunk of its next tile prefetched into registers across the block barrier, and separates phases with __syncthreads.
+// Same per-row arithmetic as k_sor_mc_packed, so the same bits.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallMaxRows = 2048;       // beyond this one SM's L2 bandwidth loses to the cooperative kernel (measured: 3969 rows 0.56 vs 0.37 ms)
+
+template <int LPR, int ITER>
+__global__ void __launch_bounds__(kSmallThreads, 1) k_sor_mc_small(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,
+                                                                   const int* __restrict__ colour_ptr, int ncolours, int iters,
+                                                                   const double* __restrict__ b, double* __restrict__ x, double omega, int xlen) {
+  extern __shared__ __align__(16) double small_smem[];
+  double* xs = small_smem;
+  double* bs = small_smem + xlen;
+  for (int i = threadIdx.x; i < xlen; i += kSmallThreads) { xs[i] = x[i]; bs[i] = b[i]; }
+  const int lane = threadIdx.x & 31, gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  constexpr int TR = (kSmallThreads / 32) * GPW;                     // rows per pass of the CTA
+  const int slot = (threadIdx.x >> 5) * GPW + lane / LPR;
+  const unsigned long long stream = policy_evict_last();            // the operator of a small level lives in L2
+  double v[ITER], nv[ITER];
+  int c[ITER], nc[ITER];
+  auto fetch = [&](int colour, int tile) {
+    const int first = colour_ptr[colour], count = colour_ptr[colour + 1] - first;
+    const int i = tile * TR + slot;
+    const bool valid = i < count;
+    const double* pv = reinterpret_cast<const double*>(chunks + (size_t)(first + (valid ? i : 0)) * chunk_bytes);
+    const int* pc = reinterpret_cast<const int*>(pv + W);
+#pragma unroll
+    for (int t = 0; t < ITER; t++) {
+      const int k = gl + t * LPR;
+      const bool ok = valid && k < W;
+      nv[t] = ok ? ldg_stream_f64(pv + k, stream) : 0.0;
+      nc[t] = ok ? ldg_stream_s32(pc + k, stream) : -1;
+    }
+  };
+  const int nphases = iters * ncolours;
+  bool pending = false;
+  __syncthreads();
+  for (int p = 0; p < nphases; p++) {
+    const int col = p % ncolours, ncol = col + 1 == ncolours ? 0 : col + 1;
+    const int ntiles = (colour_ptr[col + 1] - colour_ptr[col] + TR - 1) / TR;
+    const int nntiles = p + 1 < nphases ? (colour_ptr[ncol + 1] - colour_ptr[ncol] + TR - 1) / TR : 0;
+    for (int tile = 0; tile < ntiles; tile++) {
+      if (!pending) fetch(col, tile);
+#pragma unroll
+      for (int t = 0; t < ITER; t++) { v[t] = nv[t]; c[t] = nc[t]; }
+      pending = false;
+      if (tile + 1 < ntiles) { fetch(col, tile + 1); pending = true; }
+      else if (nntiles > 0) { fetch(ncol, 0); pending = true; }      // crosses the barrier: the operator is read-only
+      double a = 0.0, x0 = 0.0;
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        const double xv = c[t] >= 0 ? xs[c[t]] : 0.0;
+        if (t == 0) x0 = xv;
+        if (t == 0 && gl == 0) continue;
+        a = __dsub_rn(a, __dmul_rn(v[t], xv));
+      }
+      a = group_sum<LPR>(a, gmask);
+      if (gl == 0 && c[0] >= 0) {
+        double xi = __dadd_rn(a, bs[c[0]]);
+        xi = __dmul_rn(xi, omega / v[0]);
+        xi = __dadd_rn(xi, __dmul_rn(1 - omega, x0));
+        xs[c[0]] = xi;
+      }
+    }
+    if (!pending && nntiles > 0) { fetch(ncol, 0); pending = true; }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < xlen; i += kSmallThreads) x[i] = xs[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Region-synchronised multicolour sweep (fifth generation).  After packing, a colour phase is ~5 us of streaming
+// followed by a grid-wide barrier whose cost (barrier + drain + refill, ~4.6 us per phase, 220 phases per call) is
+// of the same size.  The packed rows are therefore cut into S spatial regions (consecutive ranges of the Z-curve,
+// equal row counts), one per co-resident CTA, stored region-major / colour-minor.  CTA s owns region s for the whole
+// call and runs its colours in order; before phase p it only waits until the regions its stencils touch have
+// finished phase p-1 (done[s'] >= p).  Because the region adjacency is symmetric this keeps exactly the
+// multicolour semantics -- a row of colour c sees colours < c of this sweep and colours > c of the previous one --
+// so the result is bit-identical to the barrier version, while neighbouring CTAs drift by at most one phase and
+// nobody waits for the slowest CTA of the grid.  Cooperative launch guarantees co-residency; the CTA with the
+// fewest finished phases can always run, so the waits cannot deadlock; a clock64 watchdog turns a bug into
+// MMG_ERR_TIMEOUT instead of a hung GPU.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_region_adjacency(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W, const int* __restrict__ row_region,
+                                   const int* __restrict__ node_region, int total, int S, unsigned* __restrict__ adj) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int s = row_region[i];
+  const int* pc = reinterpret_cast<const int*>(chunks + (size_t)i * chunk_bytes + (size_t)W * 8);
+  int last = s;
+  for (int k = 0; k < W; k++) {
+    const int t = node_region[pc[k]];
+    if (t >= 0 && t != s && t != last) { atomicOr(&adj[(size_t)s * ((S + 31) / 32) + (t >> 5)], 1u << (t & 31)); last = t; }
+  }
+}
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kBlock) k_sor_mc_regions(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,
+                                                           const int* __restrict__ blk_ptr, int ncolours, int iters,
+                                                           const int* __restrict__ nbr_ptr, const int* __restrict__ nbr, unsigned* done, unsigned epoch,
+                                                           const double* __restrict__ b, double* x, double omega, int* abort_flag,
+                                                           long long timeout_cycles) {
+  const int s = blockIdx.x;
+  const int n0 = nbr_ptr[s], nn = nbr_ptr[s + 1] - n0;
+  const long long t_start = clock64();
+  __shared__ int aborted;
+  if (threadIdx.x == 0) aborted = 0;
+  __syncthreads();
+  unsigned p = epoch;
+  for (int it = 0; it < iters; it++)
+    for (int c = 0; c < ncolours; c++, p++) {
+      // every region whose nodes my stencils read (or whose stencils read mine) has finished the previous phase
+      for (int k = threadIdx.x; k < nn; k += kBlock) {
+        const unsigned* flag = done + nbr[n0 + k];
+        // relaxed polls (an acquire load per spin would invalidate the SM's L1 under the other CTAs' gathers), one fence after
+        while ((int)(ld_relaxed_u32(flag) - p) < 0) {
+          if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = 1; break; }
+        }
+      }
+      if (threadIdx.x < nn) __threadfence();
+      __syncthreads();
+      if (aborted) return;
+      const int first = blk_ptr[s * ncolours + c], count = blk_ptr[s * ncolours + c + 1] - first;
+      if (count > 0) {
+        const int lane = threadIdx.x & 31;
+        const int gl = lane % LPR;
+        const unsigned gmask = group_mask<LPR>(lane);
+        constexpr int GPW = 32 / LPR;
+        constexpr int TR = (kBlock / 32) * GPW * ROWS;
+        const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
+        const unsigned char* base = chunks + (size_t)first * chunk_bytes;
+        for (int t0 = 0; t0 < count; t0 += TR) {
+          double v[ROWS][ITER], xx[ROWS][ITER], bi[ROWS], acc[ROWS];
+          int cc[ROWS][ITER];
+          bool valid[ROWS];
+#pragma unroll
+          for (int h = 0; h < ROWS; h++) {
+            const int i = t0 + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
+            valid[h] = i < count;
+            const double* pv = reinterpret_cast<const double*>(base + (size_t)(valid[h] ? i : 0) * chunk_bytes);
+            const int* pc = reinterpret_cast<const int*>(pv + W);
+#pragma unroll
+            for (int t = 0; t < ITER; t++) {
+              const int k = gl + t * LPR;
+              const bool ok = valid[h] && k < W;
+              v[h][t] = ok ? ldg_stream_f64(pv + k, stream) : 0.0;
+              cc[h][t] = ok ? ldg_stream_s32(pc + k, stream) : -1;
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < ROWS; h++)
+#pragma unroll
+            for (int t = 0; t < ITER; t++) xx[h][t] = cc[h][t] >= 0 ? ldg_keep(x + cc[h][t], keep) : 0.0;
+#pragma unroll
+          for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && valid[h]) ? b[cc[h][0]] : 0.0;
+#pragma unroll
+          for (int h = 0; h < ROWS; h++) {
+            double a = 0.0;
+#pragma unroll
+            for (int t = 0; t < ITER; t++) {
+              if (t == 0 && gl == 0) continue;
+              a = __dsub_rn(a, __dmul_rn(v[h][t], xx[h][t]));
+            }
+            acc[h] = a;
+          }
+#pragma unroll
+          for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+          if (gl == 0) {
+#pragma unroll
+            for (int h = 0; h < ROWS; h++) {
+              if (valid[h]) {
+                double xi = __dadd_rn(acc[h], bi[h]);
+                xi = __dmul_rn(xi, omega / v[h][0]);
+                xi = __dadd_rn(xi, __dmul_rn(1 - omega, xx[h][0]));
+                x[cc[h][0]] = xi;
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();                                  // every store of this phase has been issued by the CTA
+      if (threadIdx.x == 0) { __threadfence(); st_release_u32(done + s, p + 1); }
+    }
+}
+
 __global__ void k_scatter(const int* __restrict__ idx, const double* __restrict__ vals, int count, double* dst, int use_zero) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) dst[idx[i]] = use_zero ? 0.0 : vals[i];
@@ -1491,13 +1692,14 @@ void dispatch_lpr(int W, F&& f) {
 
 // (lanes per row, entries per lane) for the second-generation fast kernels; false if the width is outside the table
 template <class F>
-bool dispatch_lpr_iter(int W, F&& f) {
-  const int lpr = lanes_for_width(W);
+bool dispatch_lpr_iter(int W, F&& f, int prefer_lpr = 0) {
+  int lpr = prefer_lpr ? prefer_lpr : lanes_for_width(W);
+  { static int forced = -2; if (forced == -2) { const char* e = getenv("MMG_FAST_LPR"); forced = e ? atoi(e) : 0; } if (forced == 8 || forced == 16 || forced == 32) lpr = forced; }
   const int iter = (W + lpr - 1) / lpr;
 #define MMG_CASE(L_, I_) if (lpr == L_ && iter == I_) { f(std::integral_constant<int, L_>(), std::integral_constant<int, I_>()); return true; }
   MMG_CASE(32, 2) MMG_CASE(32, 3) MMG_CASE(32, 4)
   MMG_CASE(16, 2) MMG_CASE(16, 3)
-  MMG_CASE(8, 1) MMG_CASE(8, 2) MMG_CASE(8, 3)
+  MMG_CASE(8, 1) MMG_CASE(8, 2) MMG_CASE(8, 3) MMG_CASE(8, 4) MMG_CASE(8, 5)
 #undef MMG_CASE
   return false;
 }
@@ -2082,6 +2284,51 @@ void op_sor(Grid& g, int smoother) {
   if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && !g.neumann && L.n_ovf == 0 && L.diag_first && g.props.iters >= 1 &&
       (int)g.hx.size() == g.n && env_int("MMG_MC_PACKED", 1) && !env_int("MMG_MC_PER_COLOUR", 0)) {
     ensure_mc_pack(g);
+    if (g.mc_regions > 0) {
+      bool ok = false;
+      {
+        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
+        ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+          constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+          void* kern = (void*)k_sor_mc_regions<LPR, ITER, kMcRows>;
+          const unsigned char* chunks = g.mc_chunks.p;
+          size_t cb = L.chunk_bytes;
+          int W = L.W;
+          const int* bp = g.mc_blk_ptr.p;
+          int nc = g.n_colours, iters = g.props.iters;
+          const int* np = g.mc_nbr_ptr.p;
+          const int* nb = g.mc_nbr.p;
+          unsigned* dn = g.mc_done.p;
+          unsigned epoch = g.mc_epoch;
+          const double* b = g.b.p;
+          double* x = g.x.p;
+          double omega = g.props.omega;
+          int* abortp = g.abort_flag.p;
+          long long timeout = 6000000000ll;
+          void* args[] = {&chunks, &cb, &W, &bp, &nc, &iters, &np, &nb, &dn, &epoch, &b, &x, &omega, &abortp, &timeout};
+          MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(g.mc_regions), dim3(kBlock), args, 0, g.stream));
+          g.mc_epoch += (unsigned)(nc * iters);
+        });
+      }
+      if (ok) return;
+    }
+    if (g.A <= kSmallMaxRows && env_int("MMG_MC_SMALL", 1)) {
+      bool ok = false;
+      {
+        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
+        ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+          constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+          auto kern = k_sor_mc_small<LPR, ITER>;
+          const size_t smem = (size_t)g.A * 16;
+          static bool configured = false;
+          if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxRows * 16)); configured = true; }
+          kern<<<1, kSmallThreads, smem, g.stream>>>(g.mc_chunks.p, L.chunk_bytes, L.W, g.colour_ptr_dev.p, g.n_colours, g.props.iters, g.b.p, g.x.p,
+                                                      g.props.omega, g.A);
+          MMG_CUDA(cudaGetLastError());
+        });
+      }
+      if (ok) return;
+    }
     bool done = false;
     {
       TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
@@ -2106,7 +2353,7 @@ void op_sor(Grid& g, int smoother) {
         double omega = g.props.omega;
         void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega};
         MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
-      });
+      }, (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0);   // 8 lanes per row on the big levels: 4 rows per gather instruction share lines (+5 %)
     }
     if (done) return;
   }
@@ -2480,6 +2727,84 @@ void build_colouring(Grid& g) {
   g.mc_chunks.release();
 }
 
+// Region-major packed copy + region adjacency for k_sor_mc_regions.  `rows` holds every coloured row, colour-major and
+// in Z-curve order inside a colour.  Returns false (caller falls back to the barrier kernel) when no region count
+// gives adjacency lists short enough to poll.
+static bool mc_build_regions(Grid& g, const std::vector<int>& rows) {
+  const int nc = g.n_colours, total = (int)rows.size();
+  int max_resident = 0;
+  const bool known = dispatch_lpr_iter(g.Lap.W, [&](auto Lc, auto I) {
+    constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+    int per_sm = 0;
+    MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_mc_regions<LPR, ITER, kMcRows>, kBlock, 0));
+    max_resident = per_sm * sm_count_of(g.device);
+  });
+  if (!known || max_resident < 1) return false;
+  // Z-curve rank of every coloured row: merge the per-colour sorted lists by key
+  double x0 = g.hx[0], x1 = g.hx[0], y0 = g.hy[0], y1 = g.hy[0];
+  for (int i = 0; i < g.n; i++) { x0 = std::min(x0, g.hx[i]); x1 = std::max(x1, g.hx[i]); y0 = std::min(y0, g.hy[i]); y1 = std::max(y1, g.hy[i]); }
+  const double sx = x1 > x0 ? 65535.0 / (x1 - x0) : 0.0, sy = y1 > y0 ? 65535.0 / (y1 - y0) : 0.0;
+  auto spread = [](uint32_t v) {
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+    return v;
+  };
+  std::vector<std::pair<uint32_t, int>> keyed(total);
+  for (int k = 0; k < total; k++) {
+    const int r = rows[k];
+    keyed[k] = {spread((uint32_t)((g.hx[r] - x0) * sx)) | (spread((uint32_t)((g.hy[r] - y0) * sy)) << 1), r};
+  }
+  std::sort(keyed.begin(), keyed.end());
+  const int rows_per_region = std::max(16, env_int("MMG_MC_REGION_ROWS", 48));
+  int S = std::min(max_resident, std::max(1, total / rows_per_region));
+  const int cap = env_int("MMG_MC_REGION_CAP", 0);
+  if (cap > 0) S = std::min(S, cap);
+  for (int attempt = 0; attempt < 6 && S >= 1; attempt++, S = std::max(1, S / 2)) {
+    std::vector<int> node_region(g.A, -1), blk(static_cast<size_t>(S) * nc + 1, 0);
+    for (int k = 0; k < total; k++) node_region[keyed[k].second] = (int)((long long)k * S / total);
+    for (int k = 0; k < total; k++) { const int r = keyed[k].second; blk[(size_t)node_region[r] * nc + g.colour_host[r] + 1]++; }
+    for (size_t q = 0; q + 1 < blk.size(); q++) blk[q + 1] += blk[q];
+    std::vector<int> order(total), row_region(total), cur(blk.begin(), blk.end() - 1);
+    for (int k = 0; k < total; k++) {                       // Z-curve order survives inside every (region, colour) block
+      const int r = keyed[k].second;
+      const int dst = cur[(size_t)node_region[r] * nc + g.colour_host[r]]++;
+      order[dst] = r; row_region[dst] = node_region[r];
+    }
+    DevBuf<int> drows, drr, dnr;
+    drows.upload(order, g.stream); drr.upload(row_region, g.stream); dnr.upload(node_region, g.stream);
+    g.mc_chunks.alloc((size_t)total * g.Lap.chunk_bytes);
+    const long long threads = (long long)total * 32;
+    k_pack_chunks<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, g.stream>>>(g.Lap.chunks.p, g.Lap.chunk_bytes, drows.p, total, g.mc_chunks.p);
+    MMG_CUDA(cudaGetLastError());
+    const int words = (S + 31) / 32;
+    DevBuf<unsigned> dadj;
+    dadj.alloc((size_t)S * words); dadj.zero(g.stream);
+    k_region_adjacency<<<(total + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, drr.p, dnr.p, total, S, dadj.p);
+    MMG_CUDA(cudaGetLastError());
+    std::vector<unsigned> adj = dadj.to_host(g.stream);
+    auto bit = [&](int a, int b2) { return (adj[(size_t)a * words + (b2 >> 5)] >> (b2 & 31)) & 1u; };
+    std::vector<int> nptr(S + 1, 0), nlist;
+    int longest = 0;
+    for (int a = 0; a < S; a++) {
+      for (int b2 = 0; b2 < S; b2++) if (b2 != a && (bit(a, b2) || bit(b2, a))) nlist.push_back(b2);
+      nptr[a + 1] = (int)nlist.size();
+      longest = std::max(longest, nptr[a + 1] - nptr[a]);
+    }
+    if (longest > kBlock && S > 1) continue;                // polls are spread over the CTA's threads: keep it to one round
+    if (nlist.empty()) nlist.push_back(0);
+    g.mc_blk_ptr.upload(blk, g.stream);
+    g.mc_nbr_ptr.upload(nptr, g.stream);
+    g.mc_nbr.upload(nlist, g.stream);
+    g.mc_done.alloc(S); g.mc_done.zero(g.stream);
+    g.mc_epoch = 0;
+    MMG_CUDA(cudaStreamSynchronize(g.stream));
+    g.mc_regions = S;
+    g.mc_packed = true;
+    return true;
+  }
+  return false;
+}
+
 // Colour-major packed copy of laplaceMat_ for k_sor_mc_packed: the rows of every colour in Morton (Z-curve) order of
 // their node coordinates, so that consecutive rows of a colour form compact 2-D patches.
 void ensure_mc_pack(Grid& g) {
@@ -2509,6 +2834,8 @@ void ensure_mc_pack(Grid& g) {
       for (int k = a; k < e; k++) rows[k] = keyed[k - a].second;
     }
   }
+  g.mc_regions = 0;
+  if (env_int("MMG_MC_REGIONS", 0) && total > 0 && mc_build_regions(g, rows)) return;
   DevBuf<int> drows;
   drows.upload(rows, g.stream);
   g.mc_chunks.alloc((size_t)total * g.Lap.chunk_bytes);

@@ -146,3 +146,26 @@ def test_block_lexicographic_with_one_block_is_the_reference_sweep(libmmg):
     b.set_smoother(capi.BLOCK_LEXICOGRAPHIC); b.set_block_size(1 << 20)
     a.vCycle(8); b.vCycle(8)
     assert np.array_equal(a.residuals_, b.residuals_)
+
+
+def test_fast_multicolour_sweep_variants_are_bit_identical(libmmg, monkeypatch):
+    """The throughput-mode multicolour sweep has four schedules of the same arithmetic: colour lists over the natural
+    operator with grid barriers, the colour-major packed copy with grid barriers (plus the single-CTA shared-memory kernel
+    on levels of at most 8192 rows), and the region-major packed copy with neighbour-only synchronisation (DESIGN.md
+    section 6).  Rows of one colour are independent, so all three must produce
+    the same bits -- a stale read across regions would show up here."""
+    from meshlessmultigridpoisson_b200.problems import make_hierarchy
+
+    results = []
+    for env in ({"MMG_MC_PACKED": "0"}, {}, {"MMG_MC_SMALL": "0"}, {"MMG_MC_REGIONS": "1"}, {"MMG_MC_REGIONS": "1", "MMG_MC_REGION_ROWS": "16"}):
+        for k in ("MMG_MC_PACKED", "MMG_MC_REGIONS", "MMG_MC_REGION_ROWS", "MMG_MC_SMALL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        mg = make_hierarchy([19, 38, 75, 150, 300], "dirichlet", 4)
+        mg.set_smoother(capi.MULTICOLOUR); mg.set_arithmetic(capi.ARITH_FAST); mg.set_omega(0.8)
+        mg.vCycle(8)
+        results.append((np.array(mg.residuals_), mg.grid(-1).values_))
+    for hist, vals in results[1:]:
+        assert np.array_equal(hist, results[0][0]) and np.array_equal(vals, results[0][1])
+    assert results[0][0][-1] < 0.6 * results[0][0][0]
