@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TOL = 1e-8
-NCU_TRAFFIC_FINEST_SOR_LAUNCH = 9192000000 + 49000000   # bytes, see profiles/ (refreshed with every kernel change)
+NCU_TRAFFIC_FINEST_SOR_LAUNCH = 9509521000 + 31907328   # bytes read + written by one launch, profiles/r01_sor_mc_packed_4M_ncu.txt
 
 
 def level_sides(side, levels=None):
@@ -275,14 +275,14 @@ def main():
     src[:] = fine.source_
     val[:] = fine.values_
     for _ in range(2):
-        fine.source_ = src; fine.values_ = val; mg.vCycle(1); val[:] = fine.values_
+        fine.source_ = src; fine.values_ = val; mg.vCycle(1); fine.read_values(val)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         fine.source_ = src            # H2D
         fine.values_ = val            # H2D
         mg.vCycle(1)
-        val[:] = fine.values_         # D2H
+        fine.read_values(val)         # D2H straight into the pinned buffer
         res = mg.residuals_[-1:]      # D2H of the step's residual entry
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps

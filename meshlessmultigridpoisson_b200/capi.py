@@ -234,6 +234,12 @@ class Grid:
     def values_(self):
         return self._getv(self.L.mmg_grid_get_values)
 
+    def read_values(self, out):
+        """values_ straight into a caller-owned buffer (e.g. pinned host memory): one D2H copy, no intermediate array."""
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.A_size
+        _ck(self.L, self.L.mmg_grid_get_values(self.h, out))
+        return out
+
     @values_.setter
     def values_(self, v):
         v = _f64(v)

@@ -1407,7 +1407,10 @@ __device__ __forceinline__ void mc_phase_packed(const unsigned char* __restrict_
 #pragma unroll
     for (int h = 0; h < ROWS; h++)
 #pragma unroll
-      for (int t = 0; t < ITER; t++) xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
+      for (int t = 0; t < ITER; t++) {
+        if (c[h][t] != -1) c[h][t] &= 0x7fffffff;          // bit 31 marks "neighbour of a lower colour" for k_sor_mc_flow
+        xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
+      }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && valid[h]) ? b[c[h][0]] : 0.0;   // slot 0 is the diagonal: its column is the row
 #pragma unroll
@@ -1450,6 +1453,121 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_packed(const unsigned char* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Barrier-free multicolour sweep (sixth generation): the values are the ready flags.
+// The packed kernel loses ~4 us per colour phase to grid.sync() + drain + refill (22 phases per sweep at n=37) and
+// another ~12 % to quantisation (7.04 tiles per CTA means some CTAs run 8).  Here every sweep writes its own
+// version of the vector, xs[s+1], whose swept rows start as the sentinel NaN of the lexicographic kernels: a row of
+// colour c in sweep s reads neighbours of a lower colour from xs[s+1] (bit 31 of the packed column, set once when
+// the copy is built) and everything else from xs[s], polling with ld.relaxed.gpu while it sees the sentinel.  No
+// barrier, no fence: CTAs run from one colour into the next, a row only waits for the handful of rows it really
+// depends on, and those were scheduled a whole phase earlier.  Tiles never span two colours, tiles are dealt
+// round-robin in (sweep, colour, tile) order and every CTA walks its tiles in that order, so the lowest unfinished
+// tile always has a resident owner whose operands are complete: no deadlock under a cooperative launch; clock64
+// watchdog as in the lexicographic kernels.  Arithmetic per row identical to k_sor_mc_packed.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mark_lower_colour(unsigned char* chunks, size_t chunk_bytes, int W, int total, const int* __restrict__ colour) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int* pc = reinterpret_cast<int*>(chunks + (size_t)i * chunk_bytes + (size_t)W * 8);
+  const int own = colour[pc[0]];                              // slot 0 is the diagonal
+  for (int k = 1; k < W; k++) {
+    const int cn = colour[pc[k]];
+    if (cn >= 0 && cn < own) pc[k] |= 0x80000000;
+  }
+}
+
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,
+                                                        const int* __restrict__ colour_ptr, int ncolours, int iters, const double* __restrict__ b,
+                                                        double* xs, size_t stride, double omega, int* abort_flag, long long timeout_cycles) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  constexpr int TR = (kBlock / 32) * GPW * ROWS;
+  const unsigned long long stream = policy_evict_first();
+  const long long t_start = clock64();
+  for (int it = 0; it < iters; it++) {
+    const double* xold = xs + (size_t)it * stride;
+    double* xnew = xs + (size_t)(it + 1) * stride;
+    for (int c = 0; c < ncolours; c++) {
+      const int first = colour_ptr[c], count = colour_ptr[c + 1] - first;
+      const unsigned char* base = chunks + (size_t)first * chunk_bytes;
+      const int ntiles = (count + TR - 1) / TR;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        double v[ROWS][ITER], xx[ROWS][ITER], bi[ROWS], acc[ROWS];
+        int cc[ROWS][ITER];
+        unsigned pend = 0, newer = 0;
+#pragma unroll
+        for (int h = 0; h < ROWS; h++) {
+          const int i = tile * TR + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
+          const bool valid = i < count;
+          const double* pv = reinterpret_cast<const double*>(base + (size_t)(valid ? i : 0) * chunk_bytes);
+          const int* pc = reinterpret_cast<const int*>(pv + W);
+#pragma unroll
+          for (int t = 0; t < ITER; t++) {
+            const int k = gl + t * LPR;
+            const bool ok = valid && k < W;
+            v[h][t] = ok ? ldg_stream_f64(pv + k, stream) : 0.0;
+            cc[h][t] = ok ? ldg_stream_s32(pc + k, stream) : -1;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < ROWS; h++)
+#pragma unroll
+          for (int t = 0; t < ITER; t++) {
+            const int raw = cc[h][t];
+            if (raw != -1) {
+              cc[h][t] = raw & 0x7fffffff;
+              if (raw < 0) newer |= 1u << (h * ITER + t);
+              xx[h][t] = ld_relaxed((raw < 0 ? xnew : xold) + cc[h][t]);
+              if (is_sentinel(xx[h][t])) pend |= 1u << (h * ITER + t);
+            } else xx[h][t] = 0.0;
+          }
+#pragma unroll
+        for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && cc[h][0] != -1) ? b[cc[h][0]] : 0.0;
+        bool aborted = false;
+        while (__any_sync(0xffffffffu, pend != 0)) {            // rare: an operand of this tile is still being computed
+#pragma unroll
+          for (int h = 0; h < ROWS; h++)
+#pragma unroll
+            for (int t = 0; t < ITER; t++)
+              if (pend & (1u << (h * ITER + t))) {
+                xx[h][t] = ld_relaxed(((newer >> (h * ITER + t)) & 1u ? xnew : xold) + cc[h][t]);
+                if (!is_sentinel(xx[h][t])) pend &= ~(1u << (h * ITER + t));
+              }
+          if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
+        }
+#pragma unroll
+        for (int h = 0; h < ROWS; h++) {
+          double a = 0.0;
+#pragma unroll
+          for (int t = 0; t < ITER; t++) {
+            if (t == 0 && gl == 0) continue;
+            a = __dsub_rn(a, __dmul_rn(v[h][t], xx[h][t]));
+          }
+          acc[h] = a;
+        }
+#pragma unroll
+        for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+        if (gl == 0) {
+#pragma unroll
+          for (int h = 0; h < ROWS; h++) {
+            if (cc[h][0] != -1) {
+              double xi = __dadd_rn(acc[h], bi[h]);
+              xi = __dmul_rn(xi, omega / v[h][0]);
+              xi = __dadd_rn(xi, __dmul_rn(1 - omega, xx[h][0]));
+              st_relaxed(xnew + cc[h][0], aborted ? 0.0 : xi);      // on abort: unblock everyone behind us
+            }
+          }
+        }
+        if (aborted) return;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small levels.  Below ~10^4 rows a colour phase is a handful of rows per SM and the cooperative kernel is pure latency:
 // ~1.7 us per phase (grid barrier + an L2 round trip each for chunk, gather and store), 160-220 phases per call, 0.4 ms
 // per level and cycle -- the four coarsest levels cost as much as the whole 1M-row level.  Here ONE CTA of 1024 threads
@@ -1487,7 +1605,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sor_mc_small(const unsigne
       const int k = gl + t * LPR;
       const bool ok = valid && k < W;
       nv[t] = ok ? ldg_stream_f64(pv + k, stream) : 0.0;
-      nc[t] = ok ? ldg_stream_s32(pc + k, stream) : -1;
+      nc[t] = ok ? (ldg_stream_s32(pc + k, stream) & 0x7fffffff) : -1;
     }
   };
   const int nphases = iters * ncolours;
@@ -1547,7 +1665,7 @@ __global__ void k_region_adjacency(const unsigned char* __restrict__ chunks, siz
   const int* pc = reinterpret_cast<const int*>(chunks + (size_t)i * chunk_bytes + (size_t)W * 8);
   int last = s;
   for (int k = 0; k < W; k++) {
-    const int t = node_region[pc[k]];
+    const int t = node_region[pc[k] & 0x7fffffff];
     if (t >= 0 && t != s && t != last) { atomicOr(&adj[(size_t)s * ((S + 31) / 32) + (t >> 5)], 1u << (t & 31)); last = t; }
   }
 }
@@ -1617,7 +1735,10 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_regions(const unsigned char* 
 #pragma unroll
           for (int h = 0; h < ROWS; h++)
 #pragma unroll
-            for (int t = 0; t < ITER; t++) xx[h][t] = cc[h][t] >= 0 ? ldg_keep(x + cc[h][t], keep) : 0.0;
+            for (int t = 0; t < ITER; t++) {
+              if (cc[h][t] != -1) cc[h][t] &= 0x7fffffff;
+              xx[h][t] = cc[h][t] >= 0 ? ldg_keep(x + cc[h][t], keep) : 0.0;
+            }
 #pragma unroll
           for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && valid[h]) ? b[cc[h][0]] : 0.0;
 #pragma unroll
@@ -2329,6 +2450,42 @@ void op_sor(Grid& g, int smoother) {
       }
       if (ok) return;
     }
+    if (g.mc_regions == 0 && g.A <= env_int("MMG_MC_FLOW_MAX_ROWS", 1500000) && env_int("MMG_MC_FLOW", 1)) {
+      bool ok = false;
+      {
+        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 3);
+        const int iters = g.props.iters;
+        const size_t stride = ((size_t)g.A + 63) / 64 * 64;
+        if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
+        ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+          constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+          k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
+          MMG_CUDA(cudaGetLastError());
+          const int rows_used = env_int("MMG_MC_FLOW_ROWS", 1) == 1 ? 1 : 2;   // latency-bound levels: one row per lane group keeps more warps resident
+          void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1> : (void*)k_sor_mc_flow<LPR, ITER, 2>;
+          int blocks_per_sm = 0;
+          MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
+          const int sms = sm_count_of(g.device);
+          int maxcount = 0;
+          for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.colour_ptr[c + 1] - g.colour_ptr[c]);
+          int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, rows_used));
+          const unsigned char* chunks = g.mc_chunks.p;
+          size_t cb = L.chunk_bytes, st = stride;
+          int W = L.W;
+          const int* cp = g.colour_ptr_dev.p;
+          int nc = g.n_colours, itn = iters;
+          const double* b = g.b.p;
+          double* xs = g.xs.p;
+          double omega = g.props.omega;
+          int* abortp = g.abort_flag.p;
+          long long timeout = 6000000000ll;
+          void* args[] = {&chunks, &cb, &W, &cp, &nc, &itn, &b, &xs, &st, &omega, &abortp, &timeout};
+          MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+          MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
+        }, (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0);
+      }
+      if (ok) return;
+    }
     bool done = false;
     {
       TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
@@ -2843,6 +3000,11 @@ void ensure_mc_pack(Grid& g) {
     const long long threads = (long long)total * 32;
     k_pack_chunks<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, g.stream>>>(g.Lap.chunks.p, g.Lap.chunk_bytes, drows.p, total, g.mc_chunks.p);
     MMG_CUDA(cudaGetLastError());
+    DevBuf<int> dcol;
+    dcol.upload(g.colour_host, g.stream);
+    k_mark_lower_colour<<<(total + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, total, dcol.p);
+    MMG_CUDA(cudaGetLastError());
+    MMG_CUDA(cudaStreamSynchronize(g.stream));
   }
   MMG_CUDA(cudaStreamSynchronize(g.stream));
   g.mc_packed = true;

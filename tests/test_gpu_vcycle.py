@@ -157,8 +157,8 @@ def test_fast_multicolour_sweep_variants_are_bit_identical(libmmg, monkeypatch):
     from meshlessmultigridpoisson_b200.problems import make_hierarchy
 
     results = []
-    for env in ({"MMG_MC_PACKED": "0"}, {}, {"MMG_MC_SMALL": "0"}, {"MMG_MC_REGIONS": "1"}, {"MMG_MC_REGIONS": "1", "MMG_MC_REGION_ROWS": "16"}):
-        for k in ("MMG_MC_PACKED", "MMG_MC_REGIONS", "MMG_MC_REGION_ROWS", "MMG_MC_SMALL"):
+    for env in ({"MMG_MC_PACKED": "0"}, {}, {"MMG_MC_FLOW": "0"}, {"MMG_MC_SMALL": "0"}, {"MMG_MC_REGIONS": "1"}, {"MMG_MC_REGIONS": "1", "MMG_MC_REGION_ROWS": "16"}):
+        for k in ("MMG_MC_PACKED", "MMG_MC_REGIONS", "MMG_MC_REGION_ROWS", "MMG_MC_SMALL", "MMG_MC_FLOW"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
