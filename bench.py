@@ -257,13 +257,16 @@ def main():
     shares = {k: round(v["ms"] / max(1e-9, sum(x["ms"] for x in tm_all.values())), 4) for k, v in tm_all.items()}
     traffic, per_launch = None, None
     if fast:
-        per_launch = sor["bytes"] // max(1, sor["launches"])          # one launch = all nu sweeps of one smoothing call on the finest level
+        per_launch = sor["bytes"] // max(1, 2 * args.steps)           # one launch = all nu sweeps of one smoothing call on the finest level (this rank's rows)
         if args.side == 2000 and args.fine_poly == 4 and world == 1:
             # dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full (profiles/r01_sor_mc_packed_4M_ncu.txt)
             traffic = NCU_TRAFFIC_FINEST_SOR_LAUNCH
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_sor_mc_packed (finest level: all colours of all nu sweeps in one cooperative launch over the colour-major packed operator; "
-                          "achieved = algorithmic bytes of those launches / their CUDA-event time)"
+                "kernel": ("k_sor_mc_flow (finest level, this rank's row block: all colours of all nu sweeps in one barrier-free cooperative launch, rows next to a "
+                           "cut stored into the neighbour rank's vectors over NVLink peer memory; achieved = this rank's algorithmic bytes / CUDA-event time "
+                           "of init + sweep + halo collection)" if world > 1 else
+                           "k_sor_mc_packed (finest level: all colours of all nu sweeps in one cooperative launch over the colour-major packed operator; "
+                           "achieved = algorithmic bytes of those launches / their CUDA-event time)")
                 if fast else "k_sor_lex_chunk (finest level)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch, "bytes_per_sweep": sor["bytes"] // max(1, 2 * 5 * args.steps),
                 "sor_share_of_step": shares.get("sor"), "class_shares": shares,
@@ -299,8 +302,10 @@ def main():
         "setup_s": setup_s,
     }
     if world > 1:
-        line["comm"] = dict(mg.comm_stats(), parallelism="row-block partition of levels >= %d rows, NCCL send/recv halos per colour phase, "
-                                                         "allreduce for the norm, smaller levels replicated" % args.partition_threshold)
+        line["comm"] = dict(mg.comm_stats(), parallelism="row-block partition of levels >= %d rows; smoother halos travel inside the sweep kernel as stores "
+                                                         "into the neighbour's vectors over NVLink peer memory (NCCL send/recv per colour phase if IPC is unavailable); "
+                                                         "NCCL send/recv halos for residual / restriction / prolongation, allreduce for the norm; smaller levels "
+                                                         "replicated" % args.partition_threshold)
 
     # ---- solve to 1e-8 from a zero guess (collective: every rank takes part when the problem is partitioned)
     if not args.skip_solve:

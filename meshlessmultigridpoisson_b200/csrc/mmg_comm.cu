@@ -91,7 +91,67 @@ void comm_init(Solver& s, int rank, int world, const char* id128) {
   s.nccl_comm = c;
 }
 
+// The versioned-vector allocation of every partitioned level is exported with cudaIpcGetMemHandle, the 64-byte handles
+// travel through NCCL (a grouped broadcast per level, so the C-ABI needs no side channel), and every rank maps the
+// allocations of the ranks it sends halo values to.  Any failure leaves peer_ready false: the NCCL exchange path stays.
+void peer_setup(Solver& s) {
+  NcclApi& n = nccl();
+  const int W = s.world;
+  for (size_t l = 0; l < s.grids.size(); l++) {
+    LevelDist& D = s.dist[l];
+    if (!D.partitioned) continue;
+    Grid& g = *s.grids[l];
+    int usable = (D.x_plan.sends.size() <= 2 && g.props.iters >= 1) ? 1 : 0;
+    D.peer_iters = std::max(g.props.iters, 1);
+    D.peer_stride = ((size_t)g.A + 63) / 64 * 64;
+    D.peer_xs.alloc((size_t)2 * (D.peer_iters + 1) * D.peer_stride);
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, D.peer_xs.p) != cudaSuccess) { cudaGetLastError(); usable = 0; std::memset(&mine, 0, sizeof(mine)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DevBuf<unsigned char> dh;
+    dh.alloc((size_t)W * 72);
+    std::vector<unsigned char> hh((size_t)W * 72, 0);
+    std::memcpy(hh.data() + (size_t)s.rank * 72, &mine, 64);
+    hh[(size_t)s.rank * 72 + 64] = (unsigned char)usable;
+    dh.upload(hh, g.stream);
+    MMG_NCCL(n.GroupStart());
+    for (int r = 0; r < W; r++) MMG_NCCL(n.Broadcast(dh.p + (size_t)r * 72, dh.p + (size_t)r * 72, 72, /*ncclUint8*/ 1, r, (ncclComm_t)s.nccl_comm, g.stream));
+    MMG_NCCL(n.GroupEnd());
+    hh = dh.to_host(g.stream);
+    bool all = true;
+    for (int r = 0; r < W; r++) all = all && hh[(size_t)r * 72 + 64] == 1;
+    D.n_sends = 0;
+    if (all) {
+      for (const ExchangePlan::Msg& m : D.x_plan.sends) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, hh.data() + (size_t)m.peer * 72, 64);
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all = false; break; }
+        D.send_lo[D.n_sends] = m.offset; D.send_hi[D.n_sends] = m.offset + m.count; D.send_base[D.n_sends] = (double*)ptr;
+        D.n_sends++;
+      }
+    }
+    // every rank must agree, otherwise one side would wait for stores the other never makes
+    s.sums.zero(g.stream);
+    if (!all) { const double one = 1.0; MMG_CUDA(cudaMemcpyAsync(s.sums.p, &one, sizeof(double), cudaMemcpyHostToDevice, g.stream)); }
+    peer_init_sets(g, D);
+    allreduce_sum(s, s.sums.p, 1);                          // also orders every rank's initialisation before anybody's first store
+    double failed = 0;
+    s.sums.download(&failed, 1, g.stream);
+    D.peer_ready = failed == 0.0;
+    D.peer_parity = 0;
+  }
+}
+
+void peer_teardown(Solver& s) {
+  for (LevelDist& D : s.dist) {
+    for (int k = 0; k < D.n_sends; k++) if (D.send_base[k]) { cudaIpcCloseMemHandle(D.send_base[k]); D.send_base[k] = nullptr; }
+    D.n_sends = 0; D.peer_ready = false;
+  }
+}
+
 void comm_destroy(Solver& s) {
+  peer_teardown(s);
   if (s.nccl_comm) { nccl().CommDestroy((ncclComm_t)s.nccl_comm); s.nccl_comm = nullptr; }
 }
 

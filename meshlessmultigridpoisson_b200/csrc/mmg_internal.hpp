@@ -177,6 +177,9 @@ struct Grid {
   DevBuf<int> colour_ptr_dev;            // colour_ptr on the device (persistent multicolour kernel)
   std::vector<int> colour_host;          // per-row colour (-1 skipped)
   std::vector<int> colour_rows_host;     // host copy of colour_rows (multi-GPU sub-ranges)
+  int mc_row0 = 0, mc_row1 = -1;         // rows the packed copy covers (a rank's block on a partitioned level; -1 = all)
+  std::vector<int> mc_colour_ptr;        // colour offsets inside the packed copy
+  DevBuf<int> mc_colour_ptr_dev;
   bool mc_packed = false;
   DevBuf<unsigned char> mc_chunks;       // colour-major packed copy of Lap.chunks (Morton order inside a colour), fast multicolour sweep
   int mc_regions = 0;                    // > 0: mc_chunks is region-major (k_sor_mc_regions), one region per co-resident CTA
@@ -221,6 +224,22 @@ struct LevelDist {
   ExchangePlan r_plan;                           // entries of this level's residual that my restriction rows read
   ExchangePlan p_plan;                           // entries of the coarser level's values_ that my prolongation rows read
   std::vector<std::pair<int, int>> colour_sub;   // per colour: (first, count) of my rows inside colour_rows
+  // Peer-memory smoother: two sets of (iters+1) versioned vectors in an IPC-shared allocation; the
+  // barrier-free sweep stores a boundary row's new value into the neighbour rank's copy as well (the value is the flag).
+  bool peer_ready = false;
+  int peer_iters = 0;                            // versions per set - 1
+  size_t peer_stride = 0;
+  DevBuf<double> peer_xs;                        // 2 x (peer_iters+1) x peer_stride
+  int peer_parity = 0;                           // which set the next smoothing call uses (same sequence on every rank)
+  int n_sends = 0;                               // <= 2 neighbours
+  int send_lo[2] = {0, 0}, send_hi[2] = {0, 0};
+  double* send_base[2] = {nullptr, nullptr};     // the neighbour's peer_xs (cudaIpcOpenMemHandle)
+};
+// by-value kernel argument of the peer-memory sweep
+struct PeerSends {
+  int n;
+  int lo[2], hi[2];
+  double* base[2];
 };
 
 struct Solver {
@@ -260,6 +279,9 @@ void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P);
 void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class);
 void build_colouring(Grid& g);
 void ensure_mc_pack(Grid& g);
+void peer_setup(Solver& s);          // mmg_comm.cu: IPC exchange of the versioned-vector allocations of the partitioned levels
+void peer_teardown(Solver& s);
+void peer_init_sets(Grid& g, LevelDist& D);   // mmg_kernels.cu: both sets start as sentinels on the swept rows
 void build_block_colouring(Grid& g);
 void compute_lex_levels(Grid& g, std::vector<int>& level, int& n_levels);
 

@@ -56,6 +56,9 @@ __device__ __forceinline__ double ld_relaxed(const double* p) {
   asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 __device__ __forceinline__ void st_relaxed(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
@@ -1479,7 +1482,8 @@ __global__ void k_mark_lower_colour(unsigned char* chunks, size_t chunk_bytes, i
 template <int LPR, int ITER, int ROWS>
 __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,
                                                         const int* __restrict__ colour_ptr, int ncolours, int iters, const double* __restrict__ b,
-                                                        double* xs, size_t stride, double omega, int* abort_flag, long long timeout_cycles) {
+                                                        double* xs, size_t stride, double omega, int* abort_flag, long long timeout_cycles,
+                                                        PeerSends peers) {
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const unsigned gmask = group_mask<LPR>(lane);
@@ -1557,7 +1561,12 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __r
               double xi = __dadd_rn(acc[h], bi[h]);
               xi = __dmul_rn(xi, omega / v[h][0]);
               xi = __dadd_rn(xi, __dmul_rn(1 - omega, xx[h][0]));
-              st_relaxed(xnew + cc[h][0], aborted ? 0.0 : xi);      // on abort: unblock everyone behind us
+              const int row = cc[h][0];
+              if (aborted) xi = 0.0;                                // on abort: unblock everyone behind us
+              st_relaxed(xnew + row, xi);
+              // multi-GPU: a row next to a cut also lands in the neighbour rank's copy of this version, over NVLink
+              for (int k = 0; k < peers.n; k++)
+                if (row >= peers.lo[k] && row < peers.hi[k]) st_relaxed_sys(peers.base[k] + (size_t)(it + 1) * stride + row, xi);
             }
           }
         }
@@ -2403,7 +2412,7 @@ void op_sor(Grid& g, int smoother) {
     if (!g.have_blocks) build_block_colouring(g);
   }
   if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && !g.neumann && L.n_ovf == 0 && L.diag_first && g.props.iters >= 1 &&
-      (int)g.hx.size() == g.n && env_int("MMG_MC_PACKED", 1) && !env_int("MMG_MC_PER_COLOUR", 0)) {
+      (int)g.hx.size() == g.n && g.mc_row1 < 0 && env_int("MMG_MC_PACKED", 1) && !env_int("MMG_MC_PER_COLOUR", 0)) {
     ensure_mc_pack(g);
     if (g.mc_regions > 0) {
       bool ok = false;
@@ -2443,7 +2452,7 @@ void op_sor(Grid& g, int smoother) {
           const size_t smem = (size_t)g.A * 16;
           static bool configured = false;
           if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxRows * 16)); configured = true; }
-          kern<<<1, kSmallThreads, smem, g.stream>>>(g.mc_chunks.p, L.chunk_bytes, L.W, g.colour_ptr_dev.p, g.n_colours, g.props.iters, g.b.p, g.x.p,
+          kern<<<1, kSmallThreads, smem, g.stream>>>(g.mc_chunks.p, L.chunk_bytes, L.W, g.mc_colour_ptr_dev.p, g.n_colours, g.props.iters, g.b.p, g.x.p,
                                                       g.props.omega, g.A);
           MMG_CUDA(cudaGetLastError());
         });
@@ -2467,19 +2476,20 @@ void op_sor(Grid& g, int smoother) {
           MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
           const int sms = sm_count_of(g.device);
           int maxcount = 0;
-          for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.colour_ptr[c + 1] - g.colour_ptr[c]);
+          for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.mc_colour_ptr[c + 1] - g.mc_colour_ptr[c]);
           int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, rows_used));
           const unsigned char* chunks = g.mc_chunks.p;
           size_t cb = L.chunk_bytes, st = stride;
           int W = L.W;
-          const int* cp = g.colour_ptr_dev.p;
+          const int* cp = g.mc_colour_ptr_dev.p;
           int nc = g.n_colours, itn = iters;
           const double* b = g.b.p;
           double* xs = g.xs.p;
           double omega = g.props.omega;
           int* abortp = g.abort_flag.p;
           long long timeout = 6000000000ll;
-          void* args[] = {&chunks, &cb, &W, &cp, &nc, &itn, &b, &xs, &st, &omega, &abortp, &timeout};
+          PeerSends peers{};
+          void* args[] = {&chunks, &cb, &W, &cp, &nc, &itn, &b, &xs, &st, &omega, &abortp, &timeout, &peers};
           MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
           MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
         }, (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0);
@@ -2498,12 +2508,12 @@ void op_sor(Grid& g, int smoother) {
         MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
         const int sms = sm_count_of(g.device);
         int maxcount = 0;
-        for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.colour_ptr[c + 1] - g.colour_ptr[c]);
+        for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.mc_colour_ptr[c + 1] - g.mc_colour_ptr[c]);
         int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, rows_used));
         const unsigned char* chunks = g.mc_chunks.p;
         size_t cb = L.chunk_bytes;
         int W = L.W;
-        const int* cp = g.colour_ptr_dev.p;
+        const int* cp = g.mc_colour_ptr_dev.p;
         int nc = g.n_colours, iters = g.props.iters;
         const double* b = g.b.p;
         double* x = g.x.p;
@@ -2711,7 +2721,8 @@ std::vector<std::pair<int, int>> column_needs(Grid& ctx, const HybMatrix& M, con
 
 void dist_setup(Solver& s) {
   const int L = (int)s.grids.size(), W = s.world;
-  s.dist.assign(L, LevelDist());
+  s.dist.clear();
+  s.dist.resize(L);
   if (s.sums.n < 2) s.sums.alloc(2);
   for (int l = 0; l < L; l++) {
     Grid& g = *s.grids[l];
@@ -2744,6 +2755,7 @@ void dist_setup(Solver& s) {
     if (s.dist[l - 1].partitioned) plan_build(D.p_plan, s.rank, W, column_needs(fine, *s.prolong_[l - 1], D.bounds), s.dist[l - 1].bounds);
     (void)coarse;
   }
+  if (W > 1 && env_int("MMG_DIST_PEER", 1)) peer_setup(s);
   s.dist_ready = true;
 }
 
@@ -2774,12 +2786,116 @@ void dist_residual_norm(Solver& s, int level, double* ratio_dev) {
   MMG_CUDA(cudaGetLastError());
 }
 
+// ---- peer-memory smoother -------------------------------------------------------------------------
+// both sets: versions 1..iters of every swept row = sentinel (run once, before any rank can store into them)
+__global__ void k_peer_init_all(const unsigned char* __restrict__ rowflag, double* xs, size_t stride, int versions, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total || rowflag[i] != 0) return;
+  for (int set = 0; set < 2; set++)
+    for (int v = 1; v < versions; v++) xs[((size_t)set * versions + v) * stride + i] = __longlong_as_double((long long)kSentinelBits);
+}
+// start of a smoothing call on set `cur`: version 0 = values_; rows the sweep skips are constant in every version;
+// swept rows of versions >= 1 already hold the sentinel (or a neighbour's early store) -- they were reset one call ago,
+// which is what this launch does for the other set: nobody can touch that set before my boundary rows of THIS call
+// have reached the neighbours (they need them to finish their call), so the reset cannot overwrite live data.
+__global__ void k_peer_call_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x, double* cur, double* nxt, size_t stride,
+                                 int iters, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double xi = x[i];
+  const bool skipped = rowflag[i] != 0;
+  cur[i] = xi;
+  for (int v = 1; v <= iters; v++) {
+    if (skipped) cur[(size_t)v * stride + i] = xi;
+    nxt[(size_t)v * stride + i] = skipped ? xi : __longlong_as_double((long long)kSentinelBits);
+  }
+}
+// End of a smoothing call: my rows only waited for the halo values THEY read, so the last version of a halo row of a
+// higher colour may still be in flight from the neighbour.  Wait for each (the sentinel is the "not yet" flag) and
+// copy it into values_.  The neighbour's sweep never waits for this kernel, so it cannot deadlock.
+__global__ void k_peer_collect(const double* last, double* x, int offset, int count, int* abort_flag, long long timeout_cycles) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const long long t_start = clock64();
+  double v = ld_relaxed(last + offset + i);
+  while (is_sentinel(v)) {
+    if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); v = 0.0; break; }
+    v = ld_relaxed(last + offset + i);
+  }
+  x[offset + i] = v;
+}
+void peer_init_sets(Grid& g, LevelDist& D) {
+  k_peer_init_all<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, D.peer_xs.p, D.peer_stride, D.peer_iters + 1, g.A);
+  MMG_CUDA(cudaGetLastError());
+}
+
+// All sweeps of one smoothing call on a partitioned level in ONE launch per rank, no collective inside: the barrier-free
+// sweep over this rank's rows, whose stores next to a cut also go into the neighbour's version vectors over NVLink.
+static bool dist_sor_peer(Solver& s, Grid& g, LevelDist& D) {
+  const HybMatrix& L = g.Lap;
+  const int iters = g.props.iters;
+  if (!D.peer_ready || iters > D.peer_iters || iters < 1 || L.n_ovf != 0 || !L.diag_first) return false;
+  if (g.mc_row1 < 0 || !g.mc_packed) {
+    g.mc_row0 = D.bounds[s.rank]; g.mc_row1 = D.bounds[s.rank + 1];
+    g.mc_packed = false;
+    ensure_mc_pack(g);
+  }
+  const size_t stride = D.peer_stride, set_elems = (size_t)(D.peer_iters + 1) * stride;
+  double* cur = D.peer_xs.p + (size_t)D.peer_parity * set_elems;
+  double* nxt = D.peer_xs.p + (size_t)(D.peer_parity ^ 1) * set_elems;
+  TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * iters / s.world, 3);
+  k_peer_call_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, cur, nxt, stride, iters, g.A);
+  MMG_CUDA(cudaGetLastError());
+  const bool ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+    constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+    const int rows_used = env_int("MMG_MC_FLOW_ROWS", 1) == 1 ? 1 : 2;
+    void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1> : (void*)k_sor_mc_flow<LPR, ITER, 2>;
+    int blocks_per_sm = 0;
+    MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
+    const int sms = sm_count_of(g.device);
+    int maxcount = 0;
+    for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.mc_colour_ptr[c + 1] - g.mc_colour_ptr[c]);
+    int blocks = std::min(blocks_per_sm * sms, grid_for2(std::max(1, maxcount), LPR, sms, rows_used));
+    const unsigned char* chunks = g.mc_chunks.p;
+    size_t cb = L.chunk_bytes, st = stride;
+    int W = L.W;
+    const int* cp = g.mc_colour_ptr_dev.p;
+    int nc = g.n_colours, itn = iters;
+    const double* b = g.b.p;
+    double* xs = cur;
+    double omega = g.props.omega;
+    int* abortp = g.abort_flag.p;
+    long long timeout = 6000000000ll;
+    PeerSends peers{};
+    peers.n = D.n_sends;
+    for (int k = 0; k < D.n_sends; k++) {
+      peers.lo[k] = D.send_lo[k]; peers.hi[k] = D.send_hi[k];
+      peers.base[k] = D.send_base[k] + (size_t)D.peer_parity * set_elems;
+    }
+    void* args[] = {&chunks, &cb, &W, &cp, &nc, &itn, &b, &xs, &st, &omega, &abortp, &timeout, &peers};
+    MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+  }, (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0);
+  MMG_REQUIRE(ok, MMG_ERR_STATE, "stencil width outside the fast kernels' table");
+  // values_ <- last version: my block plus the halo ranges the neighbours mirrored into my copy
+  const double* last = cur + (size_t)iters * stride;
+  const int lo = D.bounds[s.rank], n = D.bounds[s.rank + 1] - lo;
+  MMG_CUDA(cudaMemcpyAsync(g.x.p + lo, last + lo, sizeof(double) * n, cudaMemcpyDeviceToDevice, g.stream));
+  for (const ExchangePlan::Msg& m : D.x_plan.recvs) {
+    if (m.count <= 0) continue;
+    k_peer_collect<<<(m.count + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(last, g.x.p, m.offset, m.count, g.abort_flag.p, 6000000000ll);
+    MMG_CUDA(cudaGetLastError());
+  }
+  D.peer_parity ^= 1;
+  return true;
+}
+
 void dist_sor(Solver& s, int level) {
   Grid& g = *s.grids[level];
-  const LevelDist& D = s.dist[level];
+  LevelDist& D = s.dist[level];
   if (!D.partitioned) { op_sor(g, s.smoother); return; }
   MMG_REQUIRE(s.smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact, MMG_ERR_STATE,
               "a partitioned level needs the multicolour smoother with fast arithmetic: the lexicographic sweep is a pipeline across ranks, not a partition");
+  if (dist_sor_peer(s, g, D)) return;
   const HybMatrix& L = g.Lap;
   const int sms = sm_count_of(g.device);
   for (int it = 0; it < g.props.iters; it++) {
@@ -2967,8 +3083,16 @@ static bool mc_build_regions(Grid& g, const std::vector<int>& rows) {
 void ensure_mc_pack(Grid& g) {
   if (g.mc_packed) return;
   MMG_REQUIRE(g.have_colours, MMG_ERR_STATE, "ensure_mc_pack: colouring missing");
-  const int total = g.colour_ptr[g.n_colours];
-  std::vector<int> rows(g.colour_rows_host);
+  // rows the copy covers: everything, or this rank's block of a partitioned level (mc_row0/mc_row1)
+  const int r0 = g.mc_row1 < 0 ? 0 : g.mc_row0, r1 = g.mc_row1 < 0 ? g.A : g.mc_row1;
+  std::vector<int> rows;
+  g.mc_colour_ptr.assign(g.n_colours + 1, 0);
+  for (int c = 0; c < g.n_colours; c++) {
+    for (int k = g.colour_ptr[c]; k < g.colour_ptr[c + 1]; k++) { const int r = g.colour_rows_host[k]; if (r >= r0 && r < r1) rows.push_back(r); }
+    g.mc_colour_ptr[c + 1] = (int)rows.size();
+  }
+  g.mc_colour_ptr_dev.upload(g.mc_colour_ptr, g.stream);
+  const int total = (int)rows.size();
   if (env_int("MMG_MC_ORDER", 1) == 1 && total > 0) {
     double x0 = g.hx[0], x1 = g.hx[0], y0 = g.hy[0], y1 = g.hy[0];
     for (int i = 0; i < g.n; i++) { x0 = std::min(x0, g.hx[i]); x1 = std::max(x1, g.hx[i]); y0 = std::min(y0, g.hy[i]); y1 = std::max(y1, g.hy[i]); }
@@ -2980,7 +3104,7 @@ void ensure_mc_pack(Grid& g) {
     };
     std::vector<std::pair<uint32_t, int>> keyed;
     for (int c = 0; c < g.n_colours; c++) {
-      const int a = g.colour_ptr[c], e = g.colour_ptr[c + 1];
+      const int a = g.mc_colour_ptr[c], e = g.mc_colour_ptr[c + 1];
       keyed.clear();
       for (int k = a; k < e; k++) {
         const int r = rows[k];
@@ -2992,7 +3116,7 @@ void ensure_mc_pack(Grid& g) {
     }
   }
   g.mc_regions = 0;
-  if (env_int("MMG_MC_REGIONS", 0) && total > 0 && mc_build_regions(g, rows)) return;
+  if (env_int("MMG_MC_REGIONS", 0) && total > 0 && g.mc_row1 < 0 && mc_build_regions(g, rows)) return;
   DevBuf<int> drows;
   drows.upload(rows, g.stream);
   g.mc_chunks.alloc((size_t)total * g.Lap.chunk_bytes);
