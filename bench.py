@@ -76,7 +76,7 @@ class ClockSampler:
     def __init__(self, index):
         self.lines, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -86,6 +86,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
+
+    def wait_ready(self, limit=8.0):
+        """nvidia-smi takes up to a few seconds to print its first line on a multi-GPU box; the timed region may be 40 ms."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < limit:
+            time.sleep(0.02)
 
     def mark(self):
         return time.time()
@@ -228,8 +234,9 @@ def main():
     A = fine.A_size
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps, CUDA events on the solver's stream
-    mg.vCycle(args.warmup)
     sampler = ClockSampler(local)
+    sampler.wait_ready()
+    mg.vCycle(args.warmup)
     barrier()
     mg.enable_timers(True)
     mg.reset_timers()
