@@ -1479,7 +1479,7 @@ __global__ void k_mark_lower_colour(unsigned char* chunks, size_t chunk_bytes, i
   }
 }
 
-template <int LPR, int ITER, int ROWS>
+template <int LPR, int ITER, int ROWS, bool PEER>
 __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,
                                                         const int* __restrict__ colour_ptr, int ncolours, int iters, const double* __restrict__ b,
                                                         double* xs, size_t stride, double omega, int* abort_flag, long long timeout_cycles,
@@ -1565,8 +1565,11 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __r
               if (aborted) xi = 0.0;                                // on abort: unblock everyone behind us
               st_relaxed(xnew + row, xi);
               // multi-GPU: a row next to a cut also lands in the neighbour rank's copy of this version, over NVLink
-              for (int k = 0; k < peers.n; k++)
-                if (row >= peers.lo[k] && row < peers.hi[k]) st_relaxed_sys(peers.base[k] + (size_t)(it + 1) * stride + row, xi);
+              // (constant indices: a dynamically indexed kernel parameter would be copied to local memory)
+              if (PEER) {
+                if (peers.n > 0 && row >= peers.lo[0] && row < peers.hi[0]) st_relaxed_sys(peers.base[0] + (size_t)(it + 1) * stride + row, xi);
+                if (peers.n > 1 && row >= peers.lo[1] && row < peers.hi[1]) st_relaxed_sys(peers.base[1] + (size_t)(it + 1) * stride + row, xi);
+              }
             }
           }
         }
@@ -2442,7 +2445,7 @@ void op_sor(Grid& g, int smoother) {
       }
       if (ok) return;
     }
-    if (g.A <= kSmallMaxRows && env_int("MMG_MC_SMALL", 1)) {
+    if (g.A <= std::min(kSmallMaxRows, env_int("MMG_MC_SMALL_MAX", kSmallMaxRows)) && env_int("MMG_MC_SMALL", 1)) {
       bool ok = false;
       {
         TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
@@ -2471,7 +2474,7 @@ void op_sor(Grid& g, int smoother) {
           k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
           MMG_CUDA(cudaGetLastError());
           const int rows_used = env_int("MMG_MC_FLOW_ROWS", 1) == 1 ? 1 : 2;   // latency-bound levels: one row per lane group keeps more warps resident
-          void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1> : (void*)k_sor_mc_flow<LPR, ITER, 2>;
+          void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1, false> : (void*)k_sor_mc_flow<LPR, ITER, 2, false>;
           int blocks_per_sm = 0;
           MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
           const int sms = sm_count_of(g.device);
@@ -2849,7 +2852,7 @@ static bool dist_sor_peer(Solver& s, Grid& g, LevelDist& D) {
   const bool ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
     constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
     const int rows_used = env_int("MMG_MC_FLOW_ROWS", 1) == 1 ? 1 : 2;
-    void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1> : (void*)k_sor_mc_flow<LPR, ITER, 2>;
+    void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1, true> : (void*)k_sor_mc_flow<LPR, ITER, 2, true>;
     int blocks_per_sm = 0;
     MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
     const int sms = sm_count_of(g.device);
