@@ -1588,7 +1588,7 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __r
 // Same per-row arithmetic as k_sor_mc_packed, so the same bits.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSmallThreads = 1024;
-constexpr int kSmallMaxRows = 2048;       // beyond this one SM's L2 bandwidth loses to the cooperative kernel (measured: 3969 rows 0.56 vs 0.37 ms)
+constexpr int kSmallMaxRows = 512;        // measured per cycle: 256 rows 0.17 ms (barrier-free kernel 0.16), 1024 rows 0.25 (0.17), 3969 rows 0.56 (0.18)
 
 template <int LPR, int ITER>
 __global__ void __launch_bounds__(kSmallThreads, 1) k_sor_mc_small(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,

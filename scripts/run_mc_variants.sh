@@ -1,4 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_vcycle.py -m gpu -q -x -k "variants or fast_arith" 2>&1 | tail -2
-for e in "MMG_X=1" "MMG_MC_FLOW_ROWS=2"; do
-  env $e timeout 200 python scripts/kernel_rates.py 2000 4 5 2>&1 | tail -1 | cut -c1-1000
+for e in "MMG_MC_SMALL_MAX=512" "MMG_MC_SMALL_MAX=0"; do
+  env $e timeout 200 python scripts/kernel_rates.py 2000 4 5 2>&1 | tail -1 | cut -c1-80
+  env $e timeout 200 python scripts/kernel_rates.py 2000 4 5 2>&1 | tail -1 | grep -o "L2(3969).*" | cut -c1-400
 done
