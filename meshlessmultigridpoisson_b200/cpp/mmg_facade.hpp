@@ -11,6 +11,7 @@
 #pragma once
 #include <algorithm>
 #include <stdexcept>
+#include <fstream>
 #include <string>
 #include <tuple>
 #include <utility>
@@ -285,5 +286,26 @@ class FractionalStepMultigrid : public BasicMultigrid<FractionalStepGrid> {
   FractionalStepMultigrid() : BasicMultigrid<FractionalStepGrid>(MMG_FLAVOUR_FRACSTEP) {}
   void solveLoop() {}   // empty in the reference too (FracStepMultigrid.cpp:113-115)
 };
+
+// ---- the reference's text writers, same file names and number format (std::ofstream default: 6 significant digits, one
+// value per line), so the author's plotting scripts read the files unchanged
+inline void writeVectorToTxt(const std::vector<double>& vec, const char* filename) {      // fileReadingFunctions.cpp:70-79
+  std::ofstream file;
+  file.open(filename);
+  for (size_t i = 0; i < vec.size(); i++) file << vec[i] << "\n";
+  file.close();
+}
+inline void write_temp_contour(Grid* testGrid, const std::string& directory, const std::string& extension) {   // testing_functions.cpp:285-307
+  std::vector<double> xv, yv, temp;
+  for (size_t i = 0; i < testGrid->points_.size(); i++) { xv.push_back(std::get<0>(testGrid->points_[i])); yv.push_back(std::get<1>(testGrid->points_[i])); }
+  writeVectorToTxt(xv, (directory + "x_" + extension + ".txt").c_str());
+  writeVectorToTxt(yv, (directory + "y_" + extension + ".txt").c_str());
+  for (int i = 0; i < testGrid->values_->rows() - 1; i++) temp.push_back(testGrid->values_->coeff(i));      // rows()-1, like the reference
+  writeVectorToTxt(temp, (directory + "temp_" + extension + ".txt").c_str());
+}
+template <class GridT>
+inline void write_mg_resid(BasicMultigrid<GridT>& mg, const std::string& directory, const std::string& extension) {   // testing_functions.cpp:308-312
+  writeVectorToTxt(mg.residuals_, (directory + "resid_" + extension + ".txt").c_str());
+}
 
 }  // namespace mmgf

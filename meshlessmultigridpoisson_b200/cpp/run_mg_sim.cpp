@@ -68,6 +68,11 @@ int main(int argc, char** argv) {
     for (int i = 0; i < fine->laplaceMatSize_; i++)   // calc_l1_error, testing_functions.cpp:3-16
       err += std::fabs((*fine->values_)(i) - std::sin(pi * std::get<0>(fine->points_[i])) * std::sin(pi * std::get<1>(fine->points_[i])));
     printf("l1_error %.17g\n", err / fine->laplaceMatSize_);
+    if (const char* dir = getenv("MMG_OUT_DIR")) {    // write_mg_resid + write_temp_contour, testing_functions.cpp:346-349
+      const std::string extension = std::to_string(numGrids) + "grid__L=" + std::to_string(poly_deg);
+      write_mg_resid(mg, std::string(dir) + "/", extension);
+      write_temp_contour(fine, std::string(dir) + "/", extension);
+    }
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());
     return 1;

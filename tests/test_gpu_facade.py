@@ -21,13 +21,20 @@ def test_cpp_driver_matches_python_driver_bit_for_bit(libmmg, tmp_path):
         fn = str(tmp_path / ("l%d.msh" % l))
         write_msh_nodes(fn, x, y)
         files.append(fn)
-    out = subprocess.check_output([os.path.join(cpp, "run_mg_sim"), "12", "4", *files], text=True).split("\n")
+    out = subprocess.check_output([os.path.join(cpp, "run_mg_sim"), "12", "4", *files], text=True, env=dict(os.environ, MMG_OUT_DIR=str(tmp_path))).split("\n")
     hist = np.array([float(t) for t in out[:12]])
     err = float(out[12].split()[1])
     mg = make_hierarchy(sizes, "dirichlet", 4)
     mg.vCycle(12)
     assert np.array_equal(hist, mg.residuals_)          # same library, same device-built operators: identical
     assert hist[-1] < 2e-3 * hist[0] and err < 1e-3
+    # the reference's text writers (write_mg_resid / write_temp_contour): one value per line, 6 significant digits
+    resid = np.loadtxt(tmp_path / "resid_3grid__L=4.txt")
+    assert resid.shape == hist.shape and np.allclose(resid, hist, rtol=1e-5)
+    temp = np.loadtxt(tmp_path / "temp_3grid__L=4.txt")
+    xs = np.loadtxt(tmp_path / "x_3grid__L=4.txt")
+    assert xs.size == 2500 and temp.size == 2499           # values_->rows() - 1, like the reference
+    assert np.allclose(temp, mg.grid(-1).values_[:2499], rtol=1e-5, atol=1e-12)
 
 
 def test_cpp_fracstep_driver_matches_python_driver_bit_for_bit(libmmg, tmp_path):
