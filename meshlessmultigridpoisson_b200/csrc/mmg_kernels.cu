@@ -2724,6 +2724,8 @@ std::vector<std::pair<int, int>> column_needs(Grid& ctx, const HybMatrix& M, con
 
 void dist_setup(Solver& s) {
   const int L = (int)s.grids.size(), W = s.world;
+  peer_teardown(s);                      // a repeated set-up (new threshold / communicator) starts from scratch
+  for (Grid* gp : s.grids) { gp->mc_row0 = 0; gp->mc_row1 = -1; gp->mc_packed = false; gp->mc_chunks.release(); }
   s.dist.clear();
   s.dist.resize(L);
   if (s.sums.n < 2) s.sums.alloc(2);
