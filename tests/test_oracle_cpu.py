@@ -286,6 +286,29 @@ def test_libmmg_exports_every_declared_symbol():
     assert set(names) == bound, set(names) ^ bound                      # the ctypes mirror binds exactly the header
 
 
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/mmg.h must compile as C99 (no C++-isms, no torch / CUDA types), and a C
+    program that names every declared entry point must link against libmmg.so."""
+    import re
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "mmg.h")).read()
+    names = sorted(set(re.findall(r"\b(mmg_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) > 60
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mmg.h"\n#include <stdio.h>\nint main(void) {\n  const void* p[] = {' +
+                   ", ".join("(const void*)%s" % n for n in names) + '};\n  printf("%d\\n", (int)(sizeof p / sizeof p[0]));\n  return 0;\n}\n')
+    lib = os.path.join(root, "meshlessmultigridpoisson_b200")
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-Wno-pedantic", "-I", os.path.join(root, "include"), str(src),
+                           "-L", lib, "-lmmg", "-Wl,-rpath," + lib, "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert int(out) == len(names)
+
+
 def test_no_cpu_fallback_without_a_device():
     """Host logic only: without a GPU the product must refuse, never compute on the CPU."""
     from meshlessmultigridpoisson_b200 import capi
