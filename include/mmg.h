@@ -168,8 +168,12 @@ int mmg_solver_time_vcycles(mmg_solver* s, int n_cycles, double* ms);
 
 /* ---------------------------------------------------------------- multi-GPU (no reference counterpart: the reference is serial) ---
  * One process per GPU.  Levels with at least `threshold` rows are cut into contiguous row blocks in the reference order
- * (rank r owns rows [bounds[r], bounds[r+1])); each rank sweeps only its block and exchanges the index ranges its rows read
- * with grouped ncclSend/ncclRecv; smaller levels are replicated.  Needs the multicolour smoother with fast arithmetic. */
+ * (rank r owns rows [bounds[r], bounds[r+1])); each rank works on its block only.  Residual, restriction and prolongation
+ * exchange the index ranges their rows read with grouped ncclSend/ncclRecv; the smoother needs no exchange step: its
+ * barrier-free sweep stores the rows next to a cut into the neighbour rank's vectors over NVLink peer memory (CUDA IPC,
+ * handles shipped through NCCL; falls back to per-colour NCCL exchanges if IPC is unavailable).  Smaller levels are
+ * replicated.  Needs the multicolour smoother with fast arithmetic.  After init_comm, vcycle / solve / residual are
+ * collective calls: every rank must make them in the same order. */
 int mmg_partition_bounds(int n, int world, int* bounds);                           /* the partition map (world+1 offsets), pure host */
 int mmg_comm_unique_id(char* out128);                                              /* ncclGetUniqueId on rank 0; ship the 128 bytes to every rank */
 int mmg_solver_init_comm(mmg_solver* s, int rank, int world, const char* id128);   /* ncclCommInitRank on the solver's device */
