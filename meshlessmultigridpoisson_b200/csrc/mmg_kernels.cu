@@ -2453,8 +2453,7 @@ void op_sor(Grid& g, int smoother) {
           constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
           auto kern = k_sor_mc_small<LPR, ITER>;
           const size_t smem = (size_t)g.A * 16;
-          static bool configured = false;
-          if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallMaxRows * 16)); configured = true; }
+          static_assert(kSmallMaxRows * 16 <= 48 * 1024, "beyond 48 KB the kernel needs cudaFuncAttributeMaxDynamicSharedMemorySize");
           kern<<<1, kSmallThreads, smem, g.stream>>>(g.mc_chunks.p, L.chunk_bytes, L.W, g.mc_colour_ptr_dev.p, g.n_colours, g.props.iters, g.b.p, g.x.p,
                                                       g.props.omega, g.A);
           MMG_CUDA(cudaGetLastError());
