@@ -332,3 +332,36 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".hpp", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text and "mmg_oracle" not in text, f
+
+
+def test_fracstep_operators_are_exact_on_polynomials_and_kovasznay_is_nearly_divergence_free():
+    """Known answers for the fractional-step matrices (fractionalStepGrid.cpp:60-100): every row of derivXMat_ / derivYMat_ /
+    uvLaplaceMat_ is an RBF-FD stencil with polynomial augmentation of degree polyDeg, so the assembled matrices differentiate
+    polynomials of that degree exactly at every node; applied to the analytic Kovasznay field (FractionalStepSim.cpp:96-99)
+    the discrete divergence is small."""
+    import math
+    import scipy.sparse as sp
+
+    x, y = jittered_square(28, seed=11)
+    mg = oracle.Multigrid(fracstep=True)
+    mg.add_level(oracle.KIND_PPE, x, y, 4, fine=True, dt=2e-4, mu=0.025, rho=1.0)
+    lv = mg.level(0)
+    px, py = lv.points()
+    mats = {}
+    for name, which in (("dx", oracle.MAT_DX), ("dy", oracle.MAT_DY), ("lap", oracle.MAT_UVLAP)):
+        shape, ptr, idx, val = lv.csr(which)
+        assert shape == (lv.n, lv.n)
+        mats[name] = sp.csr_matrix((val, idx, ptr), shape=shape)
+    f = 1 + 2 * px - 3 * py + px * py + 0.5 * px ** 2 - py ** 2 + px ** 3 - 2 * px * py ** 2 + 0.25 * px ** 2 * py ** 2
+    fx = 2 + py + px + 3 * px ** 2 - 2 * py ** 2 + 0.5 * px * py ** 2
+    fy = -3 + px - 2 * py - 4 * px * py + 0.5 * px ** 2 * py
+    fl = (1 + 6 * px + 0.5 * py ** 2) + (-2 - 4 * px + 0.5 * px ** 2)
+    assert np.abs(mats["dx"] @ f - fx).max() < 1e-7
+    assert np.abs(mats["dy"] @ f - fy).max() < 1e-7
+    assert np.abs(mats["lap"] @ f - fl).max() < 1e-4
+    re = 1.0 / 0.025
+    lam = 0.5 * re - math.sqrt(0.25 * re * re + 4 * math.pi ** 2)
+    u = 1 - np.exp(lam * px) * np.cos(2 * math.pi * py)
+    v = lam / (2 * math.pi) * np.exp(lam * px) * np.sin(2 * math.pi * py)
+    div = mats["dx"] @ u + mats["dy"] @ v
+    assert np.abs(div).max() < 5e-2 * np.abs(mats["dx"] @ u).max()
