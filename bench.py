@@ -336,7 +336,7 @@ def main():
             line["lexicographic"] = {"value": 1e3 / lex_ms, "unit": "V-cycles/s", "ms_per_step": lex_ms, "dag_levels_finest": nl,
                                      "note": "dependency-DAG sweep, reference-order row sums; bounded by DAG depth x L2 latency, not HBM"}
         # ---- CPU baseline beside it (bounded sample)
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:      # the CPU baseline is reported at N=1 only (rank 0 would keep the other ranks waiting)
             cores = os.cpu_count() or 1
             r = run_cpu_oracle(args.cpu_side, None, args.fine_poly, args.cpu_cycles, cores)
             scale = algorithmic_bytes_per_cycle(r["sides"], args.fine_poly) / algorithmic_bytes_per_cycle(sides, args.fine_poly)
