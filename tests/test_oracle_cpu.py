@@ -365,3 +365,25 @@ def test_fracstep_operators_are_exact_on_polynomials_and_kovasznay_is_nearly_div
     v = lam / (2 * math.pi) * np.exp(lam * px) * np.sin(2 * math.pi * py)
     div = mats["dx"] @ u + mats["dy"] @ v
     assert np.abs(div).max() < 5e-2 * np.abs(mats["dx"] @ u).max()
+
+
+def test_error_convention_of_the_c_abi():
+    """Every entry point returns an int status and records a message (the reference has no error convention at all: void
+    returns and unchecked std::vector::at, SURVEY.md section 8b).  Argument validation happens before the device is touched,
+    so these checks run without a GPU."""
+    import ctypes as C
+
+    from meshlessmultigridpoisson_b200 import capi
+
+    L = capi.load()
+    assert L.mmg_grid_destroy(None) == 0 and L.mmg_solver_destroy(None) == 0          # destroying nothing is fine, like delete nullptr
+    for fn, args, what in ((L.mmg_solver_vcycle, (None, 1), b"null argument s"), (L.mmg_grid_sor, (None, 0), b"null argument g"),
+                           (L.mmg_solver_create, (None, 0), b"null argument out"), (L.mmg_grid_fs_calc_hat, (None, -1), b"null argument g")):
+        assert fn(*args) == 1                                                         # MMG_ERR_ARG
+        assert what in L.mmg_last_error()
+    b = np.zeros(4, np.int32)
+    assert L.mmg_partition_bounds(10, 3, b) == 0 and b.tolist() == [0, 4, 7, 10]      # sizes differ by at most one, first ranks larger
+    assert L.mmg_partition_bounds(10, 0, b) == 1 and b"bad sizes" in L.mmg_last_error()
+    assert L.mmg_partition_bounds(2, 3, b) == 0 and b.tolist() == [0, 1, 2, 2]        # more ranks than rows: empty trailing blocks
+    info = C.c_char_p(L.mmg_build_info()).value if L.mmg_build_info.restype is not C.c_char_p else L.mmg_build_info()
+    assert b"sm_100a" in info
