@@ -180,6 +180,12 @@ int mmg_solver_init_comm(mmg_solver* s, int rank, int world, const char* id128);
 int mmg_solver_set_partition_threshold(mmg_solver* s, int rows);
 int mmg_solver_comm_stats(mmg_solver* s, int64_t* messages, int64_t* bytes_sent, int* partitioned_levels);
 
+/* ---------------------------------------------------------------- diagnostics (no reference counterpart) ---
+ * Used by the test-suite to prove which kernel instantiation ran and to check host-side schedules. */
+int mmg_debug_last_kernel(int slot, char* out, int cap);                           /* slot 0: last smoother kernel, 1: last SpMV-class kernel (this thread) */
+int mmg_debug_lex_trace(long long* out, int n);                                    /* clock64 stamps of the chunked lexicographic kernel (MMG_LEX_TRACE=1) */
+int mmg_debug_exchange_plan(int rank, int world, const int* need, const int* bounds, int* n_send, int* sends, int* n_recv, int* recvs); /* pure host */
+
 #ifdef __cplusplus
 }
 #endif

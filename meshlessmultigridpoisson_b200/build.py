@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mmg_kernels.cu", "mmg_assembly.cu", "mmg_api.cu", "mmg_comm.cu"]
+SOURCES = ["mmg_kernels.cu", "mmg_stream.cu", "mmg_assembly.cu", "mmg_api.cu", "mmg_comm.cu"]
 LIB = os.path.join(HERE, "libmmg.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

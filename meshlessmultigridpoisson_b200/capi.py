@@ -129,6 +129,9 @@ SIGNATURES = {
     "mmg_solver_init_comm": [_vp, _i, _i, C.c_char_p],
     "mmg_solver_set_partition_threshold": [_vp, _i],
     "mmg_solver_comm_stats": [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_i)],
+    "mmg_debug_last_kernel": [_i, C.c_char_p, _i],
+    "mmg_debug_lex_trace": [_lp, _i],
+    "mmg_debug_exchange_plan": [_i, _i, _ip, _ip, C.POINTER(_i), _ip, C.POINTER(_i), _ip],
 }
 _NON_STATUS = {"mmg_last_error": (C.c_char_p, []), "mmg_build_info": (C.c_char_p, [])}
 
@@ -583,6 +586,14 @@ class Multigrid:
         ms = _d()
         _ck(self.L, self.L.mmg_solver_time_vcycles(self.h, n, ms))
         return ms.value
+
+
+def last_kernel(slot=0):
+    """Diagnostics: the kernel instantiation the last smoother (slot 0) or SpMV-class (slot 1) call launched."""
+    L = load()
+    buf = C.create_string_buffer(128)
+    _ck(L, L.mmg_debug_last_kernel(slot, buf, 128))
+    return buf.value.decode()
 
 
 def partition_bounds(n, world):

@@ -1056,7 +1056,16 @@ int mmg_solver_reset_timers(mmg_solver* s) {
     for (int i = 0; i < MMG_T_COUNT; i++) { so.timers.ms[lv][i] = 0; so.timers.launches[lv][i] = 0; so.timers.bytes[lv][i] = 0; }
   API_END
 }
-// diagnostics, not part of include/mmg.h: clock64 stamps of one CTA of the chunked lexicographic kernel (MMG_LEX_TRACE=1)
+// diagnostics: which kernel instantiation the last smoother (slot 0) / SpMV-class (slot 1) call of this thread launched
+int mmg_debug_last_kernel(int slot, char* out, int cap) {
+  API_BEGIN
+  NEED(out);
+  MMG_REQUIRE(cap > 0 && (slot == 0 || slot == 1), MMG_ERR_ARG, "last_kernel: slot is 0 (smoother) or 1 (SpMV class)");
+  const std::string& n = last_kernel_slot(slot);
+  snprintf(out, (size_t)cap, "%s", n.c_str());
+  API_END
+}
+// diagnostics: clock64 stamps of one CTA of the chunked lexicographic kernel (MMG_LEX_TRACE=1)
 int mmg_debug_lex_trace(long long* out, int n) {
   API_BEGIN
   mmg::debug_lex_trace(out, n);
@@ -1100,7 +1109,7 @@ int mmg_solver_comm_stats(mmg_solver* s, int64_t* messages, int64_t* bytes_sent,
   if (partitioned_levels) { int n = 0; for (const LevelDist& d : S(s).dist) n += d.partitioned; *partitioned_levels = n; }
   API_END
 }
-// diagnostics (not in include/mmg.h): the exchange plan a rank derives from everybody's need intervals; pure host logic
+// diagnostics: the exchange plan a rank derives from everybody's need intervals; pure host logic
 int mmg_debug_exchange_plan(int rank, int world, const int* need, const int* bounds, int* n_send, int* sends, int* n_recv, int* recvs) {
   API_BEGIN
   std::vector<std::pair<int, int>> nd(world);

@@ -181,6 +181,7 @@ struct Grid {
   std::vector<int> mc_colour_ptr;        // colour offsets inside the packed copy
   DevBuf<int> mc_colour_ptr_dev;
   bool mc_packed = false;
+  DevBuf<int> mc_ctl;                    // tile tickets + colour-barrier arrival counters of the TMA-fed sweep (zeroed per launch)
   DevBuf<unsigned char> mc_chunks;       // colour-major packed copy of Lap.chunks (Morton order inside a colour), fast multicolour sweep
   int mc_regions = 0;                    // > 0: mc_chunks is region-major (k_sor_mc_regions), one region per co-resident CTA
   DevBuf<int> mc_blk_ptr, mc_nbr_ptr, mc_nbr;   // (region, colour) block offsets; adjacency lists of the regions
@@ -279,6 +280,10 @@ void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P);
 void op_spmv(const HybMatrix& M, const double* x_dev, double* y_dev, Grid& ctx, int timer_class);
 void build_colouring(Grid& g);
 void ensure_mc_pack(Grid& g);
+// mmg_stream.cu: TMA-fed (cp.async.bulk + mbarrier ring) multicolour sweep and SpMV-class operators; false = no instantiation
+bool stream_sor_mc(Grid& g);
+bool stream_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
+                 double* partial, int* nblocks_out, int device, cudaStream_t s, int row0, int nrows);
 void peer_setup(Solver& s);          // mmg_comm.cu: IPC exchange of the versioned-vector allocations of the partitioned levels
 void peer_teardown(Solver& s);
 void peer_init_sets(Grid& g, LevelDist& D);   // mmg_kernels.cu: both sets start as sentinels on the swept rows
@@ -309,6 +314,17 @@ struct TimedScope {
 };
 void timers_collect(Timers& t);
 void debug_lex_trace(long long* out, int n);
+// diagnostics (mmg_debug_last_kernel): the instantiation the last smoother (slot 0) / SpMV-class (slot 1) dispatch launched
+std::string& last_kernel_slot(int slot);
+inline void note_kernel_slot(int slot, const char* name, int a = -1, int b = -1, int c = -1) {
+  char buf[96];
+  if (a < 0) snprintf(buf, sizeof buf, "%s", name);
+  else if (b < 0) snprintf(buf, sizeof buf, "%s<%d>", name, a);
+  else if (c < 0) snprintf(buf, sizeof buf, "%s<%d,%d>", name, a, b);
+  else snprintf(buf, sizeof buf, "%s<%d,%d,%d>", name, a, b, c);
+  last_kernel_slot(slot) = buf;
+}
+inline void note_kernel(Grid&, const char* name, int a = -1, int b = -1, int c = -1) { note_kernel_slot(0, name, a, b, c); }
 
 // ---- multi-GPU (comm.cu, kernels.cu) ---------------------------------------------------------------
 void partition_bounds(int n, int world, int* bounds);
@@ -327,3 +343,4 @@ void dist_restrict(Solver& s, int level);
 void dist_prolong_correct(Solver& s, int level);
 
 }  // namespace mmg
+

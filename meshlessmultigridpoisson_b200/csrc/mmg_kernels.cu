@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "mmg_internal.hpp"
+#include "mmg_device.cuh"
 
 #ifndef MMG_FAST_ROWS
 #define MMG_FAST_ROWS 4
@@ -20,69 +21,6 @@
 namespace mmg {
 
 namespace {
-
-constexpr int kBlock = 256;
-constexpr unsigned long long kSentinelBits = 0xFFF8DEADBEEF0001ull;  // quiet NaN with a payload no computation produces
-
-enum { OP_SPMV = 0, OP_RESID = 1, OP_PROLONG = 2, OP_RESTRICT = 3 };
-
-__device__ __forceinline__ const double* row_val(const HybView& A, int r) {
-  return reinterpret_cast<const double*>(A.chunks + (size_t)r * A.chunk_bytes);
-}
-__device__ __forceinline__ const int* row_col(const HybView& A, int r) {
-  return reinterpret_cast<const int*>(A.chunks + (size_t)r * A.chunk_bytes + (size_t)A.W * 8);
-}
-__device__ __forceinline__ int ovf_find(const HybView& A, int row) {  // index into ovf_rows, rows with len>W only
-  int lo = 0, hi = A.n_ovf - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (A.ovf_rows[mid] < row) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-template <int LPR>
-__device__ __forceinline__ double group_sum(double v, unsigned mask) {
-#pragma unroll
-  for (int o = LPR / 2; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(mask, v, o));
-  return v;
-}
-template <int LPR>
-__device__ __forceinline__ unsigned group_mask(int lane) {
-  if (LPR == 32) return 0xffffffffu;
-  return ((1u << LPR) - 1u) << ((lane / LPR) * LPR);
-}
-__device__ __forceinline__ double ld_relaxed(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
-  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed(double* p, double v) {
-  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ bool is_sentinel(double v) { return (unsigned long long)__double_as_longlong(v) == kSentinelBits; }
-
-// block-wide sum of two doubles; result valid in thread 0
-__device__ __forceinline__ void block_sum2(double& a, double& b) {
-  __shared__ double sa[kBlock / 32], sb[kBlock / 32];
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { sa[w] = a; sb[w] = b; }
-  __syncthreads();
-  if (w == 0) {
-    a = l < (blockDim.x >> 5) ? sa[l] : 0.0;
-    b = l < (blockDim.x >> 5) ? sb[l] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // y = op(A, x): one LPR-lane group per row, lanes stride over the row chunk.
@@ -1014,32 +952,6 @@ __global__ void __launch_bounds__(kBlock) k_bound_eval_exact(HybView A, const in
 // before any arithmetic, the matrix stream is marked evict-first in L2 and the gathered vector
 // evict-last so the 8*N-byte x stays L2 resident under the 12*nnz-byte stream.
 // ================================================================================================
-__device__ __forceinline__ unsigned long long policy_evict_last() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned long long policy_evict_first() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ double ldg_keep(const double* p, unsigned long long pol) {   // gathered vector: keep in L2
-  double v;
-  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ double ldg_stream_f64(const double* p, unsigned long long pol) {   // matrix stream: read once
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ int ldg_stream_s32(const int* p, unsigned long long pol) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-  return v;
-}
-
 // pull the chunk of a row that this lane group will process on its NEXT trip into L2 (one 128-byte line per lane)
 template <int LPR>
 __device__ __forceinline__ void prefetch_chunk_l2(const HybView& A, int row, int gl) {
@@ -1789,6 +1701,7 @@ __global__ void k_scatter(const int* __restrict__ idx, const double* __restrict_
 }
 __global__ void k_set_one(double* dst, int i, double v) { dst[i] = v; }
 
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 int lanes_for_width(int W) { return W >= 48 ? 32 : (W >= 24 ? 16 : 8); }
 
 int grid_for(int work_groups_rows, int lpr, int sm_count) {
@@ -1855,12 +1768,17 @@ void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y
     if (nblocks_out) *nblocks_out = blocks;
     k_spmv_exact<<<blocks, kBlock, 0, s>>>(M.view(), M.diag_first ? 1 : 0, x, b, y, rowflag, op, mask_d, mask_n, partial);
     MMG_CUDA(cudaGetLastError());
+    note_kernel_slot(1, "k_spmv_exact");
     return;
   }
+  if (nrows >= env_int("MMG_SPMV_TMA_MIN_ROWS", 30000) && env_int("MMG_SPMV_TMA", 1) &&
+      stream_spmv(M, x, b, y, rowflag, op, mask_d, mask_n, partial, nblocks_out, device, s, row0, nrows))
+    return;
   const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(M.W, [&](auto L, auto I) {
     constexpr int LPR = decltype(L)::value, ITER = decltype(I)::value;
     int blocks = grid_for2(nrows, LPR, sms);
     if (nblocks_out) *nblocks_out = blocks;
+    note_kernel_slot(1, "k_spmv2", LPR, ITER, kSpmvRows);
     if (fast_stage()) {
       auto kern = k_spmv2<LPR, ITER, kSpmvRows, true>;
       static bool configured = false;
@@ -2140,7 +2058,6 @@ void op_prolong_correct(Grid& fine, Grid& coarse, const HybMatrix& P) {
 }
 
 // ---- SOR -----------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static int lex_block_cap(int sms) { static int v = -2; if (v == -2) v = env_int("MMG_LEX_BLOCKS", 0); return v > 0 ? v : 2 * sms; }
 static unsigned lex_sleep_ns() { static int v = -2; if (v == -2) v = env_int("MMG_LEX_SLEEP_NS", 0); return (unsigned)v; }
 
@@ -2165,6 +2082,7 @@ static void launch_lex_chunk(Grid& g, size_t stride) {
   int* abortp = g.abort_flag.p;
   long long timeout = 6000000000ll;
   void* args[] = {&A, &rf, &b, &xs, &st, &it, &omega, &abortp, &timeout};
+  note_kernel(g, "k_sor_lex_chunk", T, K);
   MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_lex_chunk<T, K>, dim3(blocks), dim3(K * 32), args, 0, g.stream));
 }
 
@@ -2203,6 +2121,7 @@ static void launch_lex_pipe(Grid& g) {
   long long timeout = 6000000000ll;
   unsigned sleep_ns = lex_sleep_ns();
   void* args[] = {&A, &rf, &b, &xs, &st, &it, &omega, &abortp, &timeout, &sleep_ns};
+  note_kernel(g, "k_sor_lex_pipe", T);
   MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_lex_pipe<T>, dim3(blocks), dim3(kBlock), args, 0, g.stream));
   MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
 }
@@ -2452,6 +2371,7 @@ void op_sor(Grid& g, int smoother) {
         ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
           constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
           auto kern = k_sor_mc_small<LPR, ITER>;
+          note_kernel(g, "k_sor_mc_small", LPR, ITER);
           const size_t smem = (size_t)g.A * 16;
           static_assert(kSmallMaxRows * 16 <= 48 * 1024, "beyond 48 KB the kernel needs cudaFuncAttributeMaxDynamicSharedMemorySize");
           kern<<<1, kSmallThreads, smem, g.stream>>>(g.mc_chunks.p, L.chunk_bytes, L.W, g.mc_colour_ptr_dev.p, g.n_colours, g.props.iters, g.b.p, g.x.p,
@@ -2474,6 +2394,7 @@ void op_sor(Grid& g, int smoother) {
           MMG_CUDA(cudaGetLastError());
           const int rows_used = env_int("MMG_MC_FLOW_ROWS", 1) == 1 ? 1 : 2;   // latency-bound levels: one row per lane group keeps more warps resident
           void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1, false> : (void*)k_sor_mc_flow<LPR, ITER, 2, false>;
+          note_kernel(g, "k_sor_mc_flow", LPR, ITER, rows_used);
           int blocks_per_sm = 0;
           MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
           const int sms = sm_count_of(g.device);
@@ -2498,6 +2419,14 @@ void op_sor(Grid& g, int smoother) {
       }
       if (ok) return;
     }
+    if (env_int("MMG_MC_TMA", 1)) {       // default on the big levels: the TMA-fed ring (mmg_stream.cu)
+      bool ok = false;
+      {
+        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 2);
+        ok = stream_sor_mc(g);
+      }
+      if (ok) return;
+    }
     bool done = false;
     {
       TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
@@ -2506,6 +2435,7 @@ void op_sor(Grid& g, int smoother) {
         constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
         void* kern = rows_pref >= 4 ? (void*)k_sor_mc_packed<LPR, ITER, 4> : rows_pref == 1 ? (void*)k_sor_mc_packed<LPR, ITER, 1> : (void*)k_sor_mc_packed<LPR, ITER, 2>;
         const int rows_used = rows_pref >= 4 ? 4 : rows_pref == 1 ? 1 : 2;
+        note_kernel(g, "k_sor_mc_packed", LPR, ITER, rows_used);
         int blocks_per_sm = 0;
         MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
         const int sms = sm_count_of(g.device);
@@ -2568,6 +2498,11 @@ void op_sor(Grid& g, int smoother) {
     }
     op_bound_eval_neumann(g);  // grid.cpp:144
   }
+}
+
+std::string& last_kernel_slot(int slot) {
+  static thread_local std::string names[2];
+  return names[slot & 1];
 }
 
 void debug_lex_trace(long long* out, int n) {

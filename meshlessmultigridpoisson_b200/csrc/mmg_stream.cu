@@ -1,0 +1,459 @@
+// TMA-fed streaming kernels (sm_100a): the multicolour smoother of the big levels and the SpMV-class operators
+// (residual / restriction / prolongation) read the immutable operator through a shared-memory ring that one elected
+// producer thread fills with 1-D bulk copies (cp.async.bulk, completion on an mbarrier with complete_tx); eight
+// consumer warps take the row chunks out of shared memory, gather the vector from L2, fold and store.
+//
+// Why (profiles/r01_sor_mc_packed_4M_ncu.txt): the register-fed sweep was latency bound -- long_scoreboard 16.3 and
+// barrier 5.2 stalls per issue, DRAM 48 % busy with clean traffic (1.01x algorithmic): every colour phase drained the
+// memory pipeline into grid.sync() and refilled it afterwards, static tiles quantised 7.04 tiles per CTA to 8, and the
+// loads in flight were bounded by registers.  Here
+//   * the bytes in flight are bounded by shared memory (stages x tile bytes per CTA), not by registers;
+//   * the operator is immutable, only x is phase ordered: the producer runs ahead ACROSS the colour barrier, so the
+//     first tiles of colour c+1 are already resident when the barrier opens;
+//   * tiles are handed out by a per-phase ticket counter (atomicAdd, next ticket prefetched), so no CTA is left with a
+//     whole extra tile at the end of a phase;
+//   * the colour barrier is one arrival counter per phase (red.release / ld.acquire), no cooperative-groups object.
+// Arithmetic per row is the one of k_sor_mc_packed / k_spmv2 (same lane mapping, same reduction tree): same bits.
+#include <algorithm>
+#include <cstdlib>
+
+#include "mmg_device.cuh"
+#include "mmg_internal.hpp"
+
+namespace mmg {
+
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = kConsumerWarps * 32;
+constexpr int kStreamThreads = kConsumers + 32;   // + the producer warp (one elected lane issues the copies)
+constexpr int kMaxStages = 12;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {   // try_wait suspends in hardware between probes
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MMG_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MMG_DONE;\n"
+      "bra MMG_WAIT;\n"
+      "MMG_DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP), bytes a multiple of 16, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) { asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+struct RingCtl {
+  unsigned long long full[kMaxStages], empty[kMaxStages];
+  int phase[kMaxStages], row0[kMaxStages], nrows[kMaxStages];
+};
+
+__device__ __forceinline__ RingCtl* ring_setup(unsigned char* smem, int stages, unsigned tile_bytes) {
+  RingCtl* C = reinterpret_cast<RingCtl*>(smem + (size_t)stages * tile_bytes);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; s++) { mbar_init(&C->full[s], 1); mbar_init(&C->empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  return C;
+}
+
+// chunk of local row `lr` of a staged tile -> registers (lane gl of an LPR-lane group takes slots gl, gl+LPR, ...)
+template <int LPR, int ITER>
+__device__ __forceinline__ void tile_row_fetch(const unsigned char* tile, unsigned chunk_bytes, int W, int lr, bool valid, int gl, double (&v)[ITER], int (&c)[ITER]) {
+  const double* pv = reinterpret_cast<const double*>(tile + (size_t)(valid ? lr : 0) * chunk_bytes);
+  const int* pc = reinterpret_cast<const int*>(pv + W);
+#pragma unroll
+  for (int t = 0; t < ITER; t++) {
+    const int k = gl + t * LPR;
+    const bool ok = valid && k < W;
+    v[t] = ok ? pv[k] : 0.0;
+    c[t] = ok ? pc[k] : -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multicolour SOR, all colours of all sweeps of one smoothing call (Dirichlet-type grids: no regularisation row, no
+// overflow rows) over the colour-major packed copy of the operator.
+// ctl[0 .. nphases) = tile tickets, ctl[nphases .. 2 nphases) = barrier arrivals, zeroed by the host before the launch.
+// Cooperative launch (the colour barrier spins), one producer warp + eight consumer warps per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned char* __restrict__ chunks, unsigned chunk_bytes, int W,
+                                                               const int* __restrict__ colour_ptr, int ncolours, int iters,
+                                                               const double* __restrict__ b, double* x, double omega, int* ctl, int stages,
+                                                               int dynamic, int* abort_flag, long long timeout_cycles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int GPW = 32 / LPR;
+  constexpr int TR = kConsumerWarps * GPW * ROWS;      // rows per tile
+  const unsigned tile_bytes = TR * chunk_bytes;
+  RingCtl* C = ring_setup(smem, stages, tile_bytes);
+  const int nphases = iters * ncolours;
+  int* tickets = ctl;
+  int* arrivals = ctl + nphases;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kConsumerWarps) {                          // ---- producer
+    if (lane != 0) return;
+    const unsigned long long pol = policy_evict_first();
+    int s = 0;
+    unsigned par = 0;
+    int phase = 0;
+    int ticket = dynamic ? atomicAdd(&tickets[0], 1) : (int)blockIdx.x;
+    for (;;) {
+      int t = ticket, first = 0, count = 0;
+      while (phase < nphases) {                          // the ticket is stale once its phase has no tiles left
+        const int c = phase % ncolours;
+        first = colour_ptr[c];
+        count = colour_ptr[c + 1] - first;
+        if (t < (count + TR - 1) / TR) break;
+        if (++phase < nphases) t = dynamic ? atomicAdd(&tickets[phase], 1) : (int)blockIdx.x;
+      }
+      mbar_wait(&C->empty[s], par ^ 1u);
+      if (phase >= nphases) {                            // terminator
+        C->phase[s] = nphases;
+        mbar_arrive(&C->full[s]);
+        return;
+      }
+      ticket = dynamic ? atomicAdd(&tickets[phase], 1) : t + (int)gridDim.x;     // in flight while this tile is issued
+      const int r0 = first + t * TR;
+      const int n = min(TR, count - t * TR);
+      C->phase[s] = phase; C->row0[s] = r0; C->nrows[s] = n;
+      const unsigned bytes = (unsigned)n * chunk_bytes;
+      mbar_arrive_expect_tx(&C->full[s], bytes);
+      bulk_g2s(smem + (size_t)s * tile_bytes, chunks + (size_t)r0 * chunk_bytes, bytes, &C->full[s], pol);
+      if (++s == stages) { s = 0; par ^= 1u; }
+    }
+  }
+
+  // ---- consumers
+  const int gl = lane % LPR, q = lane / LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const unsigned long long keep = policy_evict_last();
+  const double om1 = 1 - omega;
+  int cur_phase = 0, s = 0;
+  unsigned par = 0;
+  for (;;) {
+    mbar_wait(&C->full[s], par);
+    const int ph = C->phase[s];
+    if (ph != cur_phase) {                               // colour barrier: every CTA has stored its rows of the phases before `ph`
+      consumer_sync();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        for (int p = cur_phase; p < ph && p < nphases; p++) red_release_add(&arrivals[p], 1);
+        if (ph < nphases) {
+          const long long t0 = clock64();
+          while (ld_acquire(&arrivals[ph - 1]) < (int)gridDim.x) {
+            // watchdog: never hang the device; the sweep is abandoned (results invalid) and the host raises MMG_ERR_TIMEOUT
+            if (*(volatile int*)abort_flag || clock64() - t0 > timeout_cycles) { atomicExch(abort_flag, 1); break; }
+          }
+        }
+      }
+      consumer_sync();
+      if (ph >= nphases) return;
+      cur_phase = ph;
+    }
+    const int n = C->nrows[s];
+    const unsigned char* tile = smem + (size_t)s * tile_bytes;
+    double v[ROWS][ITER], xx[ROWS][ITER], bi[ROWS], acc[ROWS];
+    int c[ROWS][ITER];
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      const int lr = h * (kConsumerWarps * GPW) + warp * GPW + q;
+      tile_row_fetch<LPR, ITER>(tile, chunk_bytes, W, lr, lr < n, gl, v[h], c[h]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&C->empty[s]);            // the chunks are in registers: the stage can be refilled
+    if (++s == stages) { s = 0; par ^= 1u; }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++)
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        if (c[h][t] != -1) c[h][t] &= 0x7fffffff;        // bit 31 marks "neighbour of a lower colour" for k_sor_mc_flow
+        xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
+      }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && c[h][0] >= 0) ? b[c[h][0]] : 0.0;   // slot 0 is the diagonal: its column is the row
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      double a = 0.0;
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        if (t == 0 && gl == 0) continue;
+        a = __dsub_rn(a, __dmul_rn(v[h][t], xx[h][t]));
+      }
+      acc[h] = a;
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+    if (gl == 0) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) {
+        if (c[h][0] >= 0) {
+          double xi = __dadd_rn(acc[h], bi[h]);
+          xi = __dmul_rn(xi, omega / v[h][0]);
+          xi = __dadd_rn(xi, __dmul_rn(om1, xx[h][0]));   // xx[h][0] on lane 0 is x[row] before the update
+          x[c[h][0]] = xi;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpMV-class operators over the natural-order row chunks: y = op(A, x) for rows [row0, row0 + nrows) (ops as in k_spmv2).
+// Static round-robin tiles (no inter-CTA dependency: a plain launch), same ring.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void consumer_sum2(double& a, double& b, double* scratch) {   // sum over the 256 consumer threads, valid in thread 0
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { scratch[2 * w] = a; scratch[2 * w + 1] = b; }
+  consumer_sync();
+  if (w == 0) {
+    a = l < kConsumerWarps ? scratch[2 * l] : 0.0;
+    b = l < kConsumerWarps ? scratch[2 * l + 1] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+  }
+}
+
+template <int LPR, int ITER, int ROWS>
+__global__ void __launch_bounds__(kStreamThreads) k_spmv_tma(HybView A, const double* x, const double* __restrict__ b, double* y,
+                                                             const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
+                                                             double* __restrict__ partial, int row0, int nrows, int stages) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red_scratch[2 * kConsumerWarps];
+  constexpr int GPW = 32 / LPR;
+  constexpr int TR = kConsumerWarps * GPW * ROWS;
+  const unsigned chunk_bytes = (unsigned)A.chunk_bytes;
+  const unsigned tile_bytes = TR * chunk_bytes;
+  RingCtl* C = ring_setup(smem, stages, tile_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (nrows + TR - 1) / TR;
+
+  if (warp == kConsumerWarps) {                          // ---- producer
+    if (lane != 0) return;
+    const unsigned long long pol = policy_evict_first();
+    int s = 0;
+    unsigned par = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(&C->empty[s], par ^ 1u);
+      const int r0 = row0 + tile * TR;
+      const unsigned bytes = (unsigned)min(TR, nrows - tile * TR) * chunk_bytes;
+      mbar_arrive_expect_tx(&C->full[s], bytes);
+      bulk_g2s(smem + (size_t)s * tile_bytes, A.chunks + (size_t)r0 * chunk_bytes, bytes, &C->full[s], pol);
+      if (++s == stages) { s = 0; par ^= 1u; }
+    }
+    return;
+  }
+
+  const int gl = lane % LPR, q = lane / LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const unsigned long long keep = policy_evict_last();
+  double num = 0.0, den = 0.0;
+  int s = 0;
+  unsigned par = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(&C->full[s], par);
+    const int n = min(TR, nrows - tile * TR);
+    const unsigned char* tb = smem + (size_t)s * tile_bytes;
+    double v[ROWS][ITER], xx[ROWS][ITER], acc[ROWS];
+    int c[ROWS][ITER], row[ROWS];
+    bool valid[ROWS];
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      const int lr = h * (kConsumerWarps * GPW) + warp * GPW + q;
+      valid[h] = lr < n;
+      row[h] = row0 + tile * TR + lr;
+      tile_row_fetch<LPR, ITER>(tb, chunk_bytes, A.W, lr, valid[h], gl, v[h], c[h]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&C->empty[s]);
+    if (++s == stages) { s = 0; par ^= 1u; }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++)
+#pragma unroll
+      for (int t = 0; t < ITER; t++) xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      double a = 0.0;
+#pragma unroll
+      for (int t = 0; t < ITER; t++) a = __dadd_rn(a, __dmul_rn(v[h][t], xx[h][t]));
+      acc[h] = a;
+    }
+    if (A.n_ovf) {                                       // rows longer than W (implicit-Neumann fill-in) keep their tail in a small CSR
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) {
+        if (valid[h] && A.len[row[h]] > A.W) {
+          const int o = ovf_find(A, row[h]);
+          for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) acc[h] = __dadd_rn(acc[h], __dmul_rn(A.ovf_val[k], x[A.ovf_col[k]]));
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      if (valid[h] && gl == 0) {
+        const int flag = rowflag ? rowflag[row[h]] : 0;
+        if (op == OP_SPMV) {
+          y[row[h]] = acc[h];
+        } else if (op == OP_RESID) {
+          const double bi = b[row[h]];
+          double t = __dsub_rn(bi, acc[h]);
+          if (flag == 1) t = 0.0;
+          if (y) y[row[h]] = t;
+          num += fabs(t);
+          den += fabs(bi);
+        } else if (op == OP_PROLONG) {
+          if (!(mask_dirichlet && flag == 1)) y[row[h]] = __dadd_rn(y[row[h]], acc[h]);
+        } else {
+          double t = acc[h];
+          if (flag == 1) t = 0.0;
+          if (mask_neumann && flag == 2) t = 0.0;
+          y[row[h]] = t;
+        }
+      }
+    }
+  }
+  if (partial) {
+    consumer_sum2(num, den, red_scratch);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = num; partial[2 * blockIdx.x + 1] = den; }
+  }
+}
+
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+// (lanes per row, entries per lane) table shared with the register-fed kernels
+template <class F>
+bool dispatch_lanes(int W, int prefer_lpr, F&& f) {
+  const int lpr = prefer_lpr ? prefer_lpr : (W >= 48 ? 32 : (W >= 24 ? 16 : 8));
+  const int iter = (W + lpr - 1) / lpr;
+#define MMG_CASE(L_, I_) if (lpr == L_ && iter == I_) { f(std::integral_constant<int, L_>(), std::integral_constant<int, I_>()); return true; }
+  MMG_CASE(32, 2) MMG_CASE(32, 3) MMG_CASE(32, 4)
+  MMG_CASE(16, 2) MMG_CASE(16, 3)
+  MMG_CASE(8, 1) MMG_CASE(8, 2) MMG_CASE(8, 3) MMG_CASE(8, 4) MMG_CASE(8, 5)
+#undef MMG_CASE
+  return false;
+}
+
+struct RingShape { int stages; size_t smem; int ctas_per_sm; };
+
+// Ring depth: as many stages as fit the per-CTA shared-memory budget (ctas_per_sm CTAs share an SM's 227 KB; the rest stays L1 for the gathers)
+RingShape ring_shape(unsigned tile_bytes, int ctas_per_sm, int want_stages) {
+  const size_t budget = (size_t)env_int("MMG_TMA_SMEM_KB", 120) * 1024 / (size_t)ctas_per_sm;
+  int stages = (int)((budget - sizeof(RingCtl) - 128) / tile_bytes);
+  if (want_stages > 0) stages = std::min(stages, want_stages);
+  stages = std::max(2, std::min(stages, kMaxStages));
+  return RingShape{stages, (size_t)stages * tile_bytes + sizeof(RingCtl), ctas_per_sm};
+}
+
+int sm_count(int device) {
+  static int cached[64] = {0};
+  if (device < 64 && cached[device]) return cached[device];
+  int n = 0;
+  MMG_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  if (device < 64) cached[device] = n;
+  return n;
+}
+
+template <class K>
+void allow_smem(K kern, size_t smem, int ctas_per_sm) {
+  // per-kernel attributes; setting them again is cheap and idempotent.  The carve-out hint keeps what the ring does not
+  // need as L1 for the gathers (the driver would otherwise size shared memory for the occupancy limit, not for our grid).
+  MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int pct = std::min(100, (int)((100 * (size_t)ctas_per_sm * (smem + 2048) + 228 * 1024 - 1) / (228 * 1024)));
+  MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+}
+
+}  // namespace
+
+// All colours of all props.iters sweeps of the multicolour smoother over g.mc_chunks.  Returns false when the stencil
+// width has no instantiation (the caller falls back to the register-fed kernel).
+bool stream_sor_mc(Grid& g) {
+  const HybMatrix& L = g.Lap;
+  const int prefer = (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0;     // 8 lanes per row on the big levels (as k_sor_mc_packed)
+  const int rows_pref = env_int("MMG_TMA_ROWS", 1);
+  return dispatch_lanes(L.W, prefer, [&](auto Lc, auto I) {
+    constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+    const int rows_used = rows_pref >= 2 ? 2 : 1;
+    auto kern = rows_used == 2 ? k_sor_mc_tma<LPR, ITER, 2> : k_sor_mc_tma<LPR, ITER, 1>;
+    const unsigned tile_bytes = (unsigned)(kConsumerWarps * (32 / LPR) * rows_used * L.chunk_bytes);
+    const int sms = sm_count(g.device);
+    RingShape rs = ring_shape(tile_bytes, env_int("MMG_TMA_CTAS", 2), env_int("MMG_TMA_STAGES", 0));
+    allow_smem(kern, rs.smem, rs.ctas_per_sm);
+    int blocks_per_sm = 0;
+    MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kStreamThreads, rs.smem));
+    MMG_REQUIRE(blocks_per_sm >= 1, MMG_ERR_CUDA, "k_sor_mc_tma does not fit an SM");
+    const int blocks = std::min(blocks_per_sm, rs.ctas_per_sm) * sms;
+    const int nphases = g.n_colours * g.props.iters;
+    if (g.mc_ctl.n < (size_t)2 * nphases) g.mc_ctl.alloc((size_t)2 * nphases);
+    MMG_CUDA(cudaMemsetAsync(g.mc_ctl.p, 0, sizeof(int) * 2 * nphases, g.stream));
+    const unsigned char* chunks = g.mc_chunks.p;
+    unsigned cb = (unsigned)L.chunk_bytes;
+    int W = L.W;
+    const int* cp = g.mc_colour_ptr_dev.p;
+    int nc = g.n_colours, iters = g.props.iters;
+    const double* b = g.b.p;
+    double* x = g.x.p;
+    double omega = g.props.omega;
+    int* ctl = g.mc_ctl.p;
+    int stages = rs.stages, dynamic = env_int("MMG_TMA_DYNAMIC", 1);
+    int* abortp = g.abort_flag.p;
+    long long timeout = 4000000000ll;                    // ~2 s of SM clocks per colour barrier
+    void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout};
+    note_kernel(g, "k_sor_mc_tma", LPR, ITER, rows_used);
+    MMG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(blocks), dim3(kStreamThreads), args, rs.smem, g.stream));
+  });
+}
+
+// y = op(M, x) on rows [row0, row0+nrows) through the TMA ring; false when the stencil width has no instantiation
+bool stream_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
+                 double* partial, int* nblocks_out, int device, cudaStream_t s, int row0, int nrows) {
+  const int prefer = (nrows >= 200000 && M.W > 16 && M.W <= 40) ? env_int("MMG_SPMV_TMA_LPR", 8) : 0;
+  const int rows_pref = env_int("MMG_SPMV_TMA_ROWS", 2);
+  return dispatch_lanes(M.W, prefer, [&](auto Lc, auto I) {
+    constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+    const int rows_used = rows_pref >= 2 ? 2 : 1;
+    auto kern = rows_used == 2 ? k_spmv_tma<LPR, ITER, 2> : k_spmv_tma<LPR, ITER, 1>;
+    const int TR = kConsumerWarps * (32 / LPR) * rows_used;
+    const unsigned tile_bytes = (unsigned)(TR * M.chunk_bytes);
+    const int sms = sm_count(device);
+    RingShape rs = ring_shape(tile_bytes, env_int("MMG_TMA_CTAS", 2), env_int("MMG_TMA_STAGES", 0));
+    allow_smem(kern, rs.smem, rs.ctas_per_sm);
+    const int ntiles = (nrows + TR - 1) / TR;
+    const int blocks = std::max(1, std::min(rs.ctas_per_sm * sms, ntiles));
+    if (nblocks_out) *nblocks_out = blocks;
+    note_kernel_slot(1, "k_spmv_tma", LPR, ITER, rows_used);
+    kern<<<blocks, kStreamThreads, rs.smem, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, row0, nrows, rs.stages);
+    MMG_CUDA(cudaGetLastError());
+  });
+}
+
+}  // namespace mmg

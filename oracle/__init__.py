@@ -42,10 +42,13 @@ def lib():
         "orc_mg_new": (v, [i]),
         "orc_mg_free": (None, [v]),
         "orc_mg_add_level": (i, [v, i, i, _dp, _dp, i, i, d, i, i, i, i, i, d, d, d]),
+        "orc_mg_add_level_raw": (i, [v, i, i, _dp, _dp, i, i, i, d, i, i, i, _ip, _ip, _ip, _dp, _dp, i]),
+        "orc_mg_alloc_interp": (None, [v]),
         "orc_mg_build": (i, [v]),
         "orc_mg_nlevels": (i, [v]),
         "orc_mg_set_multicolour": (None, [v, i]),
         "orc_mg_set_smoother": (None, [v, i, i]),
+        "orc_mg_set_omega": (None, [v, d]),
         "orc_lv_sor_blocklex": (None, [v, i, i]),
         "orc_lv_block_colouring": (i, [v, i, i, _ip, i]),
         "orc_mg_vcycle": (i, [v, i]),
@@ -301,6 +304,24 @@ class Multigrid:
         if rc:
             raise OracleError(self.L.orc_last_error().decode())
 
+    def add_level_raw(self, x, y, props, boundaries, source, implicit=False, fracstep_grid=False):
+        """A level whose state was built elsewhere (reordered points, boundary lists as (type, points, values), source);
+        operators follow through Level.set_csr.  Used to mirror a device-built hierarchy at sizes where the oracle's own
+        set-up would take minutes."""
+        x, y = np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64)
+        src = np.ascontiguousarray(source, np.float64)
+        bt = np.ascontiguousarray([b[0] for b in boundaries], np.int32)
+        ptr = np.ascontiguousarray(np.concatenate([[0], np.cumsum([len(b[1]) for b in boundaries])]), np.int32)
+        pts = np.ascontiguousarray(np.concatenate([b[1] for b in boundaries]) if boundaries else np.zeros(0), np.int32)
+        vals = np.ascontiguousarray(np.concatenate([b[2] for b in boundaries]) if boundaries else np.zeros(0), np.float64)
+        rc = self.L.orc_mg_add_level_raw(self.h, int(fracstep_grid), x.size, x, y, props["polyDeg"], props["stencilSize"], props["iters"],
+                                         props["omega"], props["rbfExp"], int(implicit), len(boundaries), bt, ptr, pts, vals, src, src.size)
+        if rc:
+            raise OracleError(self.L.orc_last_error().decode())
+
+    def alloc_interp(self):
+        self.L.orc_mg_alloc_interp(self.h)
+
     def build(self):
         if self.L.orc_mg_build(self.h):
             raise OracleError(self.L.orc_last_error().decode())
@@ -320,6 +341,9 @@ class Multigrid:
     def set_smoother(self, smoother, block_size=4096):
         """0 lexicographic (the reference), 1 multicolour, 2 block-lexicographic"""
         self.L.orc_mg_set_smoother(self.h, smoother, block_size)
+
+    def set_omega(self, omega):
+        self.L.orc_mg_set_omega(self.h, omega)
 
     def vcycle(self, n=1):
         if self.L.orc_mg_vcycle(self.h, n):

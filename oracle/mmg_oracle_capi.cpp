@@ -85,6 +85,42 @@ int orc_mg_add_level(void* h, int kind, int n, const double* x, const double* y,
   ORC_CATCH(-1)
 }
 
+// A level whose state (reordered points, boundary lists, flags, source) was built elsewhere -- the tests use it to mirror a
+// DEVICE-built hierarchy into the oracle at sizes where the oracle's own kNN + LU set-up would take minutes: the operators
+// then arrive through orc_lv_set_csr (identical matrices on both sides).  No reordering, no assembly.
+// btype[b] in {1 dirichlet, 2 neumann}; bptr has nb+1 entries into bpts / bvals.
+int orc_mg_add_level_raw(void* h, int fracstep_grid, int n, const double* x, const double* y, int polyDeg, int stencil, int iters, double omega,
+                         int rbfExp, int implicit, int nb, const int* btype, const int* bptr, const int* bpts, const double* bvals,
+                         const double* source, int source_len) {
+  ORC_TRY
+  std::vector<Pt> pts(n);
+  for (int i = 0; i < n; i++) pts[i] = Pt{x[i], y[i], 0.0};
+  GridProperties p;
+  p.rbfExp = rbfExp; p.polyDeg = polyDeg; p.omega = omega; p.iters = iters; p.stencilSize = stencil;
+  std::vector<Boundary> bnds(nb);
+  for (int b = 0; b < nb; b++) {
+    bnds[b].type = btype[b];
+    bnds[b].bcPoints.assign(bpts + bptr[b], bpts + bptr[b + 1]);
+    bnds[b].values.assign(bvals + bptr[b], bvals + bptr[b + 1]);
+  }
+  std::vector<double> src(source, source + source_len);
+  Grid* g = fracstep_grid ? new FractionalStepGrid(pts, bnds, p, src) : new Grid(pts, bnds, p, src);
+  g->implicitFlag_ = implicit != 0;
+  for (int b = 0; b < nb; b++) g->setBCFlag(b, btype[b] == 1 ? "dirichlet" : "neumann", bnds[b].values);
+  if ((int)g->source_.size() != g->laplaceMat_.rows) throw std::runtime_error("source length does not match the level");
+  g->order_.resize(n);
+  for (int i = 0; i < n; i++) g->order_[i] = i;
+  static_cast<Handle*>(h)->mg.addGrid(g);
+  return 0;
+  ORC_CATCH(-1)
+}
+// size the P / R slots without building them (they are then filled by orc_lv_set_csr)
+void orc_mg_alloc_interp(void* h) {
+  Multigrid& mg = static_cast<Handle*>(h)->mg;
+  mg.prolongMatrices_.assign(mg.grids_.size(), Csr());
+  mg.restrictionMatrices_.assign(mg.grids_.size(), Csr());
+}
+
 int orc_mg_build(void* h) {
   ORC_TRY
   static_cast<Handle*>(h)->mg.buildMatrices();
@@ -100,6 +136,9 @@ void orc_mg_set_smoother(void* h, int smoother, int block_size) {
   mg.blocklex = smoother == 2;
   if (smoother == 2)
     for (auto& g : mg.grids_) { g.second->block_size_ = block_size; g.second->block_colour_.clear(); }
+}
+void orc_mg_set_omega(void* h, double omega) {   // properties_.omega of every level (gridclasses.hpp:12)
+  for (auto& g : static_cast<Handle*>(h)->mg.grids_) g.second->properties_.omega = omega;
 }
 void orc_lv_sor_blocklex(void* h, int l, int block_size) {
   Grid* g = lv(h, l);

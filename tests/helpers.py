@@ -54,3 +54,35 @@ def gpu_solver_from_oracle(mg, device=0, fracstep=False):
 def random_values(lv, seed):
     rng = np.random.default_rng(seed)
     return rng.standard_normal(lv.A)
+
+
+def oracle_mirror_of_gpu(mg_gpu, kind, fine_poly, coarse_poly=3, fracstep=False, **props):
+    """Mirror a DEVICE-built hierarchy into the oracle without running the oracle's own set-up (kNN + one LU per node take
+    minutes beyond ~250k nodes): level state and operators are downloaded through the C-ABI and pushed into raw oracle
+    levels, so both sides hold identical matrices (SURVEY.md section 7 contract).  kind: 'dirichlet' | 'neumann' | 'mixed'."""
+    from meshlessmultigridpoisson_b200.problems import grid_props
+
+    L = mg_gpu.num_grids
+    mg = oracle.Multigrid(fracstep=fracstep)
+    nb = 2 if kind == "mixed" else 1
+    for l in range(L):
+        g = mg_gpu.grid(l)
+        x, y = g.points_
+        bnds = [g.boundary(b) for b in range(nb)]
+        p = grid_props(fine_poly if l == L - 1 else coarse_poly, **props)
+        mg.add_level_raw(x, y, p, bnds, g.source_, implicit=(kind != "dirichlet"))
+    for l in range(L):
+        g, lv = mg_gpu.grid(l), mg.level(l)
+        shape, ptr, idx, val = g.csr()
+        lv.set_csr(oracle.MAT_A, shape, ptr, idx, val)
+        if kind != "dirichlet":
+            shape, ptr, idx, val = g.csr(capi.MAT_NEUMANN_COEFFS)
+            lv.set_csr(oracle.MAT_NBC, shape, ptr, idx, val)
+        lv.set_vec(oracle.VEC_DIAGS, g.diags)
+        lv.set_vec(oracle.VEC_VALUES, g.values_)
+    mg.alloc_interp()
+    for l in range(1, L):
+        mg.level(l).set_csr(oracle.MAT_R, *mg_gpu.interp_csr(capi.MAT_RESTRICT, l))
+    for l in range(L - 1):
+        mg.level(l).set_csr(oracle.MAT_P, *mg_gpu.interp_csr(capi.MAT_PROLONG, l))
+    return mg

@@ -43,8 +43,7 @@ def _worker(rank, world, port, out):
         need = np.array([[max(0, b[r] - bw), min(n, b[r + 1] + bw)] for r in range(world)], np.int32).ravel()
         ns, nr = C.c_int(), C.c_int()
         sends, recvs = np.zeros(3 * world, np.int32), np.zeros(3 * world, np.int32)
-        rc = L.mmg_debug_exchange_plan(rank, world, need.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.byref(ns), sends.ctypes.data_as(C.c_void_p),
-                                       C.byref(nr), recvs.ctypes.data_as(C.c_void_p))
+        rc = L.mmg_debug_exchange_plan(rank, world, need, np.ascontiguousarray(b, np.int32), C.byref(ns), sends, C.byref(nr), recvs)
         ok &= rc == 0
         msg = torch.zeros(2, 3 * world, dtype=torch.long)
         msg[0, : 3 * ns.value] = torch.from_numpy(sends[: 3 * ns.value].astype(np.int64))
