@@ -36,7 +36,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TOL = 1e-8
-NCU_TRAFFIC_FINEST_SOR_LAUNCH = 9509521000 + 31907328   # bytes read + written by one launch, profiles/r01_sor_mc_packed_4M_ncu.txt
+
+
+def ncu_traffic(kernel, side, fine_poly):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` on this workload, read from the committed ncu
+    summary index (profiles/ncu_traffic.json, keyed kernel|side|polyDeg); None when no capture of this kernel/workload exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get("%s|%d|%d" % (kernel, side, fine_poly), {}).get("dram_bytes")
+    except (OSError, ValueError):
+        return None
+
+
+def golden_history(side, fine_poly, key):
+    """residual history of the first cycles of this workload from the CPU oracle alone (tests/make_bench_golden.py)"""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_%d_p%d.json" % (side, fine_poly))) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
 
 
 def level_sides(side, levels=None):
@@ -139,23 +157,52 @@ def run_cpu_oracle(side, levels_below, fine_poly, cycles, threads_setup):
 
 
 def reference_arm(args):
+    """The reference's own CPU implementation of the path (the oracle port, pinned bit-identical to the reference sources),
+    MEASURED on the stated workload: set-up with every host thread (untimed; the reference's O(N^2) kNN is replaced by the
+    bit-identical cell search), then `while (mg.residual() >= 1e-8) mg.vCycle();` (loop shape of FractionalStepSim.cpp:139-142)
+    from a zero guess on ONE thread, because the reference is strictly serial.  The W warm-up and K timed steps are cycles
+    W+1 .. W+K of that solve (a V-cycle costs the same whatever the iterate), each timed around exactly the call the
+    reference times (testing_functions.cpp:340-344)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import oracle
+
     cores = os.cpu_count() or 1
-    full_sides = level_sides(args.side, args.levels)
-    r = run_cpu_oracle(args.cpu_side, None, args.fine_poly, max(1, args.steps), cores)
-    scale = algorithmic_bytes_per_cycle(r["sides"], args.fine_poly) / algorithmic_bytes_per_cycle(full_sides, args.fine_poly)
-    s_full = r["s_per_cycle"] / scale            # V-cycle cost is linear in the bytes it streams
-    v = 1.0 / s_full
-    sample = ("CPU oracle (restated reference, g++ -O2 -ffp-contract=off), lexicographic SOR, %d V-cycles on a %dx%d-side hierarchy %s "
-              "(%.3f s/cycle), scaled by algorithmic bytes x%.4g to the %dx%d workload; V-cycle loop on 1 thread because the reference is serial"
-              % (max(1, args.steps), args.cpu_side, args.cpu_side, r["sides"], r["s_per_cycle"], 1 / scale, args.side, args.side))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    sides = level_sides(args.side, args.levels)
+    t0 = time.time()
+    mg = oracle.make_hierarchy(sides, kind=oracle.KIND_DIRICHLET, fine_poly=args.fine_poly)
+    setup_s = time.time() - t0
+    per_cycle, t_solve0 = [], time.perf_counter()
+    budget_s = args.ref_budget_s
+    r = mg.residual()
+    while r >= TOL and len(per_cycle) < 400:
+        per_cycle.append(mg.time_vcycles(1))
+        r = mg.residual()
+        if time.perf_counter() - t_solve0 > budget_s and len(per_cycle) >= args.warmup + args.steps:
+            break                                  # bounded run: the K timed cycles are complete, the solve is reported as unfinished
+    solve_s = time.perf_counter() - t_solve0
+    timed = per_cycle[args.warmup: args.warmup + args.steps]
+    if len(timed) < args.steps:                    # converged before W+K cycles (small workloads): time what is left of K on the converged iterate
+        timed += [mg.time_vcycles(1) for _ in range(args.steps - len(timed))]
+    s_step = sum(timed) / len(timed)
+    v = 1.0 / s_step
+    hist = mg.history()
+    rate = float((hist[min(len(hist) - 1, 20)] / hist[min(len(hist) - 1, 5)]) ** (1.0 / max(1, min(len(hist) - 1, 20) - min(len(hist) - 1, 5)))) if len(hist) > 6 else None
+    sample = ("CPU oracle (the reference's grid.cpp / multigrid.cpp restated, pinned bit-identical to the reference sources; g++ -O2 "
+              "-ffp-contract=off), MEASURED on the stated %dx%d hierarchy %s: lexicographic SOR omega=1.4, V-cycle loop on 1 thread because the "
+              "reference is serial (%d host cores present); set-up %.0f s on %d threads, untimed; steps = cycles %d..%d of the solve from a zero guess"
+              % (args.side, args.side, sides, cores, setup_s, cores, args.warmup + 1, args.warmup + args.steps))
+    cfg = workload_config(args, sides)
+    cfg["smoother"] = "lexicographic SOR omega=1.4 (the reference's own smoother) -- the GPU arm's throughput mode is multicolour SOR omega=%g; compare `solve`" % args.mc_omega
     line = {
         "impl": "reference", "metric": "vcycles_per_s", "value": v, "unit": "V-cycles/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * s_full, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, full_sides),
-        "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": cores},
+        "warmup": args.warmup, "ms_per_step": 1e3 * s_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "solve": {"tol": TOL, "cycles": len(per_cycle), "seconds": solve_s, "final_residual": r, "converged": bool(r < TOL),
+                  "mode": "lexicographic omega=1.4, 1 thread", "convergence_per_cycle": rate},
+        "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": cores, "setup_s": setup_s},
         "e2e": {"value": v, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -183,6 +230,7 @@ def main():
     ap.add_argument("--mc-omega", type=float, default=0.8, help="relaxation factor of the multicolour (throughput) mode")
     ap.add_argument("--cpu-side", type=int, default=500, help="finest lattice side of the bounded CPU sample")
     ap.add_argument("--cpu-cycles", type=int, default=3)
+    ap.add_argument("--ref-budget-s", type=float, default=900.0, help="--impl reference: stop the solve after this many seconds once the K timed cycles are done")
     ap.add_argument("--partition-threshold", type=int, default=200000, help="multi-GPU: levels with fewer rows are replicated")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-lex", action="store_true")
@@ -263,21 +311,34 @@ def main():
     achieved = sor["bytes"] / (sor["ms"] * 1e-3) / 1e9 if sor["ms"] > 0 else 0.0
     shares = {k: round(v["ms"] / max(1e-9, sum(x["ms"] for x in tm_all.values())), 4) for k, v in tm_all.items()}
     traffic, per_launch = None, None
+    kernel = capi.last_kernel(0)                                      # the instantiation the last smoothing call (finest level, up-sweep) launched
     if fast:
         per_launch = sor["bytes"] // max(1, 2 * args.steps)           # one launch = all nu sweeps of one smoothing call on the finest level (this rank's rows)
-        if args.side == 2000 and args.fine_poly == 4 and world == 1:
-            # dram__bytes_read.sum + dram__bytes_write.sum of that launch, ncu --set full (profiles/r01_sor_mc_packed_4M_ncu.txt)
-            traffic = NCU_TRAFFIC_FINEST_SOR_LAUNCH
+        if world == 1:
+            traffic = ncu_traffic(kernel, args.side, args.fine_poly)  # from the committed ncu capture of this kernel on this workload, else null
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("k_sor_mc_flow (finest level, this rank's row block: all colours of all nu sweeps in one barrier-free cooperative launch, rows next to a "
-                           "cut stored into the neighbour rank's vectors over NVLink peer memory; achieved = this rank's algorithmic bytes / CUDA-event time "
-                           "of init + sweep + halo collection)" if world > 1 else
-                           "k_sor_mc_packed (finest level: all colours of all nu sweeps in one cooperative launch over the colour-major packed operator; "
-                           "achieved = algorithmic bytes of those launches / their CUDA-event time)")
-                if fast else "k_sor_lex_chunk (finest level)",
+                "kernel": kernel + (" (finest level, this rank's row block: all colours of all nu sweeps in one launch; rows next to a cut are stored into the "
+                                    "neighbour rank's vectors over NVLink peer memory; achieved = this rank's algorithmic bytes / CUDA-event time of init + sweep "
+                                    "+ halo collection)" if world > 1 else
+                                    " (finest level: all colours of all nu sweeps of one smoothing call in one cooperative launch over the colour-major packed "
+                                    "operator, fed by cp.async.bulk through a shared-memory ring; achieved = algorithmic bytes of those launches / their "
+                                    "CUDA-event time)") if fast else kernel + " (finest level)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch, "bytes_per_sweep": sor["bytes"] // max(1, 2 * 5 * args.steps),
                 "sor_share_of_step": shares.get("sor"), "class_shares": shares,
+                "per_class_GBps": {k: (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None) for k, v in tm_fine.items() if k != "other"},
                 "whole_cycle_GBps": algorithmic_bytes_per_cycle(sides, args.fine_poly) / (ms_per_step * 1e-3) / 1e9}
+
+    # ---- in-run correctness: the first cycles of the timed configuration against the CPU oracle's golden history of this workload
+    gold = golden_history(args.side, args.fine_poly, "multicolour_omega0.8" if fast and args.mc_omega == 0.8 else "lexicographic_omega1.4" if not fast else "-")
+    hist = mg.residuals_
+    check = {"golden": None}
+    if gold is not None and args.levels is None:
+        m = min(len(gold), len(hist), 6)
+        dev = float(np.max(np.abs(hist[:m] - np.array(gold[:m])) / np.array(gold[:m])))
+        check = {"golden": "tests/golden/bench_%d_p%d.json (CPU oracle, own operators)" % (args.side, args.fine_poly), "cycles_compared": m, "max_rel_dev": dev,
+                 "tol": 1e-6, "ok": bool(dev < 1e-6)}
+        if not check["ok"]:
+            raise SystemExit("bench.py: residual history of the timed configuration deviates from the oracle's golden history: %r vs %r" % (hist[:m].tolist(), gold[:m]))
 
     # ---- end to end through the C-ABI with host buffers (pinned), copies inside the timed region
     src = torch.empty(A, dtype=torch.float64).pin_memory().numpy()
@@ -304,9 +365,9 @@ def main():
 
     line = {
         "metric": "vcycles_per_s", "value": value, "unit": "V-cycles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, sides), "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-        "setup_s": setup_s,
+        "setup_s": setup_s, "check": check,
     }
     if world > 1:
         line["comm"] = dict(mg.comm_stats(), parallelism="row-block partition of levels >= %d rows; smoother halos travel inside the sweep kernel as stores "

@@ -103,7 +103,8 @@ template <int LPR, int ITER, int ROWS>
 __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned char* __restrict__ chunks, unsigned chunk_bytes, int W,
                                                                const int* __restrict__ colour_ptr, int ncolours, int iters,
                                                                const double* __restrict__ b, double* x, double omega, int* ctl, int stages,
-                                                               int dynamic, int* abort_flag, long long timeout_cycles) {
+                                                               int dynamic, int* abort_flag, long long timeout_cycles,
+                                                               int debug_flags) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int GPW = 32 / LPR;
   constexpr int TR = kConsumerWarps * GPW * ROWS;      // rows per tile
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
       if (threadIdx.x == 0) {
         __threadfence();
         for (int p = cur_phase; p < ph && p < nphases; p++) red_release_add(&arrivals[p], 1);
-        if (ph < nphases) {
+        if (ph < nphases && !(debug_flags & 1)) {
           const long long t0 = clock64();
           while (ld_acquire(&arrivals[ph - 1]) < (int)gridDim.x) {
             // watchdog: never hang the device; the sweep is abandoned (results invalid) and the host raises MMG_ERR_TIMEOUT
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
 #pragma unroll
       for (int t = 0; t < ITER; t++) {
         if (c[h][t] != -1) c[h][t] &= 0x7fffffff;        // bit 31 marks "neighbour of a lower colour" for k_sor_mc_flow
-        xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
+        xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + ((debug_flags & 2) ? (c[h][0] & 0x7fffffff) : c[h][t]), keep) : 0.0;
       }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && c[h][0] >= 0) ? b[c[h][0]] : 0.0;   // slot 0 is the diagonal: its column is the row
@@ -357,7 +358,7 @@ bool dispatch_lanes(int W, int prefer_lpr, F&& f) {
   const int iter = (W + lpr - 1) / lpr;
 #define MMG_CASE(L_, I_) if (lpr == L_ && iter == I_) { f(std::integral_constant<int, L_>(), std::integral_constant<int, I_>()); return true; }
   MMG_CASE(32, 2) MMG_CASE(32, 3) MMG_CASE(32, 4)
-  MMG_CASE(16, 2) MMG_CASE(16, 3)
+  MMG_CASE(16, 2) MMG_CASE(16, 3) MMG_CASE(16, 4) MMG_CASE(16, 5)
   MMG_CASE(8, 1) MMG_CASE(8, 2) MMG_CASE(8, 3) MMG_CASE(8, 4) MMG_CASE(8, 5)
 #undef MMG_CASE
   return false;
@@ -366,8 +367,8 @@ bool dispatch_lanes(int W, int prefer_lpr, F&& f) {
 struct RingShape { int stages; size_t smem; int ctas_per_sm; };
 
 // Ring depth: as many stages as fit the per-CTA shared-memory budget (ctas_per_sm CTAs share an SM's 227 KB; the rest stays L1 for the gathers)
-RingShape ring_shape(unsigned tile_bytes, int ctas_per_sm, int want_stages) {
-  const size_t budget = (size_t)env_int("MMG_TMA_SMEM_KB", 120) * 1024 / (size_t)ctas_per_sm;
+RingShape ring_shape(unsigned tile_bytes, int ctas_per_sm, int want_stages, int smem_kb) {
+  const size_t budget = (size_t)smem_kb * 1024 / (size_t)ctas_per_sm;
   int stages = (int)((budget - sizeof(RingCtl) - 128) / tile_bytes);
   if (want_stages > 0) stages = std::min(stages, want_stages);
   stages = std::max(2, std::min(stages, kMaxStages));
@@ -398,15 +399,19 @@ void allow_smem(K kern, size_t smem, int ctas_per_sm) {
 // width has no instantiation (the caller falls back to the register-fed kernel).
 bool stream_sor_mc(Grid& g) {
   const HybMatrix& L = g.Lap;
-  const int prefer = (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0;     // 8 lanes per row on the big levels (as k_sor_mc_packed)
-  const int rows_pref = env_int("MMG_TMA_ROWS", 1);
+  // lanes per row on the big levels: 8 up to n=37 (as k_sor_mc_packed), 16 for the wide stencils (n=70: 4803 vs 3837 GB/s with a warp per row)
+  int prefer = g.A < 200000 ? 0 : (L.W > 16 && L.W <= 40) ? 8 : (L.W > 40 && L.W <= 80) ? 16 : 0;
+  if (env_int("MMG_TMA_LPR", 0)) prefer = env_int("MMG_TMA_LPR", 0);
+  const int rows_pref = env_int("MMG_TMA_ROWS", 2);
   return dispatch_lanes(L.W, prefer, [&](auto Lc, auto I) {
     constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
     const int rows_used = rows_pref >= 2 ? 2 : 1;
     auto kern = rows_used == 2 ? k_sor_mc_tma<LPR, ITER, 2> : k_sor_mc_tma<LPR, ITER, 1>;
     const unsigned tile_bytes = (unsigned)(kConsumerWarps * (32 / LPR) * rows_used * L.chunk_bytes);
     const int sms = sm_count(g.device);
-    RingShape rs = ring_shape(tile_bytes, env_int("MMG_TMA_CTAS", 2), env_int("MMG_TMA_STAGES", 0));
+    // measured on the 4M-row level, n=37 (profiles/r02_tma_sweep.txt): 3 CTAs x 2 stages x 64-row tiles 4789 GB/s; 2 CTAs x 3 stages 4463;
+    // 32-row tiles 3204 (2 CTAs) ... 4403 (4 CTAs): the consumers are latency bound on the gathers, so resident warps count
+    RingShape rs = ring_shape(tile_bytes, env_int("MMG_TMA_CTAS", 3), env_int("MMG_TMA_STAGES", 0), env_int("MMG_TMA_SMEM_KB", 180));
     allow_smem(kern, rs.smem, rs.ctas_per_sm);
     int blocks_per_sm = 0;
     MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kStreamThreads, rs.smem));
@@ -427,7 +432,8 @@ bool stream_sor_mc(Grid& g) {
     int stages = rs.stages, dynamic = env_int("MMG_TMA_DYNAMIC", 1);
     int* abortp = g.abort_flag.p;
     long long timeout = 4000000000ll;                    // ~2 s of SM clocks per colour barrier
-    void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout};
+    int debug_flags = env_int("MMG_TMA_DEBUG", 0);      // timing decomposition only (1: no colour barrier, 2: no gathers): results invalid
+    void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &debug_flags};
     note_kernel(g, "k_sor_mc_tma", LPR, ITER, rows_used);
     MMG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(blocks), dim3(kStreamThreads), args, rs.smem, g.stream));
   });
@@ -436,7 +442,8 @@ bool stream_sor_mc(Grid& g) {
 // y = op(M, x) on rows [row0, row0+nrows) through the TMA ring; false when the stencil width has no instantiation
 bool stream_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
                  double* partial, int* nblocks_out, int device, cudaStream_t s, int row0, int nrows) {
-  const int prefer = (nrows >= 200000 && M.W > 16 && M.W <= 40) ? env_int("MMG_SPMV_TMA_LPR", 8) : 0;
+  int prefer = nrows < 200000 ? 0 : (M.W > 16 && M.W <= 40) ? 8 : (M.W > 40 && M.W <= 80) ? 16 : 0;
+  if (env_int("MMG_SPMV_TMA_LPR", 0)) prefer = env_int("MMG_SPMV_TMA_LPR", 0);
   const int rows_pref = env_int("MMG_SPMV_TMA_ROWS", 2);
   return dispatch_lanes(M.W, prefer, [&](auto Lc, auto I) {
     constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
@@ -445,7 +452,7 @@ bool stream_spmv(const HybMatrix& M, const double* x, const double* b, double* y
     const int TR = kConsumerWarps * (32 / LPR) * rows_used;
     const unsigned tile_bytes = (unsigned)(TR * M.chunk_bytes);
     const int sms = sm_count(device);
-    RingShape rs = ring_shape(tile_bytes, env_int("MMG_TMA_CTAS", 2), env_int("MMG_TMA_STAGES", 0));
+    RingShape rs = ring_shape(tile_bytes, env_int("MMG_SPMV_TMA_CTAS", 3), env_int("MMG_SPMV_TMA_STAGES", 0), env_int("MMG_SPMV_TMA_SMEM_KB", 180));
     allow_smem(kern, rs.smem, rs.ctas_per_sm);
     const int ntiles = (nrows + TR - 1) / TR;
     const int blocks = std::max(1, std::min(rs.ctas_per_sm * sms, ntiles));

@@ -25,7 +25,7 @@ def test_level_sides():
 def _run(rank):
     env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank))
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
-                           "--cpu-side", "40", "--side", "200"], env=env, capture_output=True, text=True, timeout=600)
+                           "--side", "100"], env=env, capture_output=True, text=True, timeout=600)
 
 
 def test_reference_arm_prints_one_line_on_rank0_only():
@@ -36,4 +36,8 @@ def test_reference_arm_prints_one_line_on_rank0_only():
     assert line["impl"] == "reference" and line["metric"] == "vcycles_per_s" and line["unit"] == "V-cycles/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
-    assert line["higher_is_better"] is True and line["dtype"] == "f64"
+    assert line["higher_is_better"] is True and line["dtype"] == "f64" and line["scaling"] == "strong"
+    # the arm MEASURES the stated workload: the reference's stop rule to 1e-8 with its own smoother, timed steps inside that solve
+    assert line["solve"]["converged"] and line["solve"]["final_residual"] < 1e-8 and line["solve"]["cycles"] >= 1
+    assert "100x100" in line["config"]["workload"] and "lexicographic" in line["config"]["smoother"]
+    assert abs(line["ms_per_step"] * line["value"] - 1e3) < 1e-6

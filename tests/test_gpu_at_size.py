@@ -170,7 +170,7 @@ def test_lexicographic_history_config2(h1m, monkeypatch):
     ho, hg = ref.history()[-5:], gpu.residuals_[n0:]
     assert np.abs(hg - ho).max() / ho.min() < 1e-6 and (np.abs(hg - ho) / ho).max() < 1e-10, (hg, ho)
     assert H.rel_l2(gpu.grid(-1).values_, ref.level(-1).values) < 1e-8
-    assert ho[-1] < 0.3 * ho[0]
+    assert ho[-1] < 0.8 * ho[0]          # six levels stop at a 32x32 cloud: ~0.92 per cycle
 
 
 def test_multicolour_history_at_1m(h1m, monkeypatch):
