@@ -179,6 +179,9 @@ int mmg_comm_unique_id(char* out128);                                           
 int mmg_solver_init_comm(mmg_solver* s, int rank, int world, const char* id128);   /* ncclCommInitRank on the solver's device */
 int mmg_solver_set_partition_threshold(mmg_solver* s, int rows);
 int mmg_solver_comm_stats(mmg_solver* s, int64_t* messages, int64_t* bytes_sent, int* partitioned_levels);
+/* After a partitioned vcycle / solve, mmg_grid_get_values on a rank is current on that rank's row block and halo ranges only.
+ * This collective completes values_ of every partitioned level on every rank (call it before reading the whole solution). */
+int mmg_solver_gather_values(mmg_solver* s);
 
 /* ---------------------------------------------------------------- diagnostics (no reference counterpart) ---
  * Used by the test-suite to prove which kernel instantiation ran and to check host-side schedules. */

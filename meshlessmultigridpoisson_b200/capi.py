@@ -129,6 +129,7 @@ SIGNATURES = {
     "mmg_solver_init_comm": [_vp, _i, _i, C.c_char_p],
     "mmg_solver_set_partition_threshold": [_vp, _i],
     "mmg_solver_comm_stats": [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_i)],
+    "mmg_solver_gather_values": [_vp],
     "mmg_debug_last_kernel": [_i, C.c_char_p, _i],
     "mmg_debug_lex_trace": [_lp, _i],
     "mmg_debug_exchange_plan": [_i, _i, _ip, _ip, C.POINTER(_i), _ip, C.POINTER(_i), _ip],
@@ -490,7 +491,9 @@ class Multigrid:
             level += self.num_grids
         g = _vp()
         _ck(self.L, self.L.mmg_solver_grid(self.h, level, C.byref(g)))
-        return Grid(None, None, None, None, None, _handle=g, _owned=False)
+        w = Grid(None, None, None, None, None, _handle=g, _owned=False)
+        w._parent = self             # the wrapper must not outlive the solver that owns the grid
+        return w
 
     def buildMatrices(self):
         _ck(self.L, self.L.mmg_solver_build_matrices(self.h))
@@ -576,6 +579,10 @@ class Multigrid:
 
     def set_partition_threshold(self, rows):
         _ck(self.L, self.L.mmg_solver_set_partition_threshold(self.h, rows))
+
+    def gather_values(self):
+        """collective: complete values_ of every partitioned level on every rank (after a partitioned vCycle / solve)"""
+        _ck(self.L, self.L.mmg_solver_gather_values(self.h))
 
     def comm_stats(self):
         m, b, p = C.c_int64(), C.c_int64(), _i()

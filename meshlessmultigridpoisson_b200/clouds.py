@@ -25,6 +25,37 @@ def jittered_square(s, seed, jitter=0.3):
     return np.ascontiguousarray(x.ravel()), np.ascontiguousarray(y.ravel())
 
 
+def hex_square(s, seed=0, jitter=0.0, margin=0.3):
+    """Gmsh-frontal-like cloud on the unit square: s equispaced nodes per edge lying *exactly* on x,y in {0,1} (listed first:
+    bottom, top, left, right), hexagonally packed interior nodes at the same spacing h = 1/(s-1), none closer than
+    ``margin*h`` to a vertical edge.  About 1.15 s^2 nodes.  The reference's author meshed with Gmsh (files never committed,
+    testing_functions.cpp:355-364); on clouds of this kind the reference's scheme converges with Neumann and mixed boundaries at
+    sizes where it diverges on jittered lattices.  ``jitter`` displaces interior nodes by
+    U(-jitter*h, jitter*h) with ``numpy.random.default_rng(seed)``."""
+    h = 1.0 / (s - 1)
+    t = np.arange(s, dtype=np.float64) / (s - 1)
+    bx = np.concatenate([t, t, np.zeros(s - 2), np.ones(s - 2)])
+    by = np.concatenate([np.zeros(s), np.ones(s), t[1:-1], t[1:-1]])
+    ny = int(round(1.0 / (h * np.sqrt(3.0) / 2.0)))
+    dy = 1.0 / ny
+    rows = []
+    for j in range(1, ny):
+        xs = np.arange(0.5 * h if j % 2 else 0.0, 1.0 + 1e-12, h)
+        xs = xs[(xs > margin * h) & (xs < 1.0 - margin * h)]
+        rows.append(np.stack([xs, np.full_like(xs, j * dy)], 1))
+    P = np.concatenate(rows)
+    if jitter:
+        P = P + np.random.default_rng(seed).uniform(-jitter * h, jitter * h, P.shape)
+    return np.ascontiguousarray(np.concatenate([bx, P[:, 0]])), np.ascontiguousarray(np.concatenate([by, P[:, 1]]))
+
+
+def make_cloud(kind, s, seed, jitter=0.3):
+    """'jittered': SURVEY.md section 8d lattice; 'hex': the Gmsh-like cloud"""
+    if kind == "hex":
+        return hex_square(s, seed)
+    return jittered_square(s, seed=seed, jitter=jitter)
+
+
 def level_sizes(s_fine, n_levels):
     """Lattice sides for a hierarchy with ~4x node coarsening per level (coarsest first)."""
     out = [s_fine]

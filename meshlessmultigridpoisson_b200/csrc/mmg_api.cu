@@ -239,7 +239,11 @@ int mmg_grid_create(mmg_grid** out, int device, int n, const double* x, const do
 }
 int mmg_grid_destroy(mmg_grid* g) {
   API_BEGIN
-  if (g) { use_device(G(g).device); delete &G(g); }
+  if (g) {
+    MMG_REQUIRE(G(g).owner == nullptr, MMG_ERR_STATE, "mmg_grid_destroy: the grid is owned by a solver, which frees it (multigrid.cpp:10-16)");
+    use_device(G(g).device);
+    delete &G(g);
+  }
   API_END
 }
 int mmg_grid_set_implicit(mmg_grid* g, int flag) {
@@ -758,6 +762,8 @@ int mmg_solver_add_grid(mmg_solver* s, mmg_grid* g) {
   NEED(s); NEED(g);
   Solver& so = S(s);
   Grid* gr = &G(g);
+  MMG_REQUIRE(gr->owner == nullptr, MMG_ERR_STATE, "addGrid: the grid already belongs to a solver (Multigrid owns its grids, multigrid.cpp:10-16)");
+  gr->owner = &so;
   use_device(gr->device);
   if (!so.stream) MMG_CUDA(cudaStreamCreateWithFlags(&so.stream, cudaStreamNonBlocking));
   gr->sync();
@@ -1015,6 +1021,19 @@ int mmg_solver_solve(mmg_solver* s, double tol, int max_cycles, int extra_bound_
   solver_check_abort(so);
   if (cycles_done) *cycles_done = n;
   if (final_residual) *final_residual = r;
+  API_END
+}
+// multi-GPU: after a partitioned vcycle / solve a rank's values_ are current on its row block and halo ranges only; this
+// collective makes every partitioned level's values_ complete on every rank (grouped ncclBroadcast of the row blocks)
+int mmg_solver_gather_values(mmg_solver* s) {
+  API_BEGIN
+  NEED(s);
+  Solver& so = S(s);
+  if (so.world > 1 && so.dist_ready) {
+    use_device(so.grids[0]->device);
+    for (size_t l = 0; l < so.grids.size(); l++)
+      if (so.dist[l].partitioned) allgather_blocks(so, so.grids[l]->x.p, so.dist[l].bounds);
+  }
   API_END
 }
 int mmg_solver_sync(mmg_solver* s) {

@@ -800,7 +800,6 @@ void asm_build_laplacian(Grid& g) {
   }
   for (int i = 0; i < N + 1; i++)
     if (i == N || g.bcflags[i] != 2) trip.push_back(Trip{N, i, 1.0});
-  MMG_REQUIRE(!st.dn_point.empty() || true, MMG_ERR_STATE, "");
   {
     size_t expect = 0;
     for (const Boundary& b : g.boundaries) if (b.type == MMG_BC_NEUMANN) expect += b.pts.size();

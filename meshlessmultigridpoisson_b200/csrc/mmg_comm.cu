@@ -35,12 +35,16 @@ struct NcclApi {
 NcclApi& nccl() {
   static NcclApi api;
   if (api.handle) return api;
-  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  const char* forced = getenv("MMG_NCCL_LIB");          // tests point this at a missing file to exercise the error path
+  const char* names[] = {forced ? forced : "libnccl.so.2", forced ? forced : "libnccl.so"};
   for (const char* n : names) {
     api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (api.handle) break;
   }
-  MMG_REQUIRE(api.handle != nullptr, MMG_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found"));
+  if (!api.handle) {
+    const char* e = dlerror();                           // dlerror() clears the message: read it exactly once
+    throw Error(MMG_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + (e ? e : "not found"));
+  }
   auto sym = [&](const char* s) {
     void* p = dlsym(api.handle, s);
     MMG_REQUIRE(p != nullptr, MMG_ERR_NCCL, std::string("libnccl lacks ") + s);
@@ -58,6 +62,25 @@ NcclApi& nccl() {
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
   return api;
 }
+
+// ncclGroupStart ... ncclGroupEnd with the group closed on every path: an exception between the two must not leave the
+// communicator inside an open group
+struct NcclGroup {
+  NcclApi& n;
+  bool open = false;
+  explicit NcclGroup(NcclApi& api) : n(api) {
+    const int r = n.GroupStart();
+    if (r != ncclSuccess) throw Error(MMG_ERR_NCCL, std::string("ncclGroupStart failed: ") + n.GetErrorString(r));
+    open = true;
+  }
+  void close() {
+    if (!open) return;
+    open = false;
+    const int r = n.GroupEnd();
+    if (r != ncclSuccess) throw Error(MMG_ERR_NCCL, std::string("ncclGroupEnd failed: ") + n.GetErrorString(r));
+  }
+  ~NcclGroup() { if (open) n.GroupEnd(); }
+};
 
 #define MMG_NCCL(call)                                                                                               \
   do {                                                                                                               \
@@ -114,9 +137,11 @@ void peer_setup(Solver& s) {
     std::memcpy(hh.data() + (size_t)s.rank * 72, &mine, 64);
     hh[(size_t)s.rank * 72 + 64] = (unsigned char)usable;
     dh.upload(hh, g.stream);
-    MMG_NCCL(n.GroupStart());
-    for (int r = 0; r < W; r++) MMG_NCCL(n.Broadcast(dh.p + (size_t)r * 72, dh.p + (size_t)r * 72, 72, /*ncclUint8*/ 1, r, (ncclComm_t)s.nccl_comm, g.stream));
-    MMG_NCCL(n.GroupEnd());
+    {
+      NcclGroup grp(n);
+      for (int r = 0; r < W; r++) MMG_NCCL(n.Broadcast(dh.p + (size_t)r * 72, dh.p + (size_t)r * 72, 72, /*ncclUint8*/ 1, r, (ncclComm_t)s.nccl_comm, g.stream));
+      grp.close();
+    }
     hh = dh.to_host(g.stream);
     bool all = true;
     for (int r = 0; r < W; r++) all = all && hh[(size_t)r * 72 + 64] == 1;
@@ -176,10 +201,12 @@ void plan_build(ExchangePlan& P, int rank, int world, const std::vector<std::pai
 void plan_execute(Solver& s, const ExchangePlan& P, double* vec) {
   if (s.world == 1 || (P.sends.empty() && P.recvs.empty())) return;
   NcclApi& n = nccl();
-  MMG_NCCL(n.GroupStart());
-  for (const ExchangePlan::Msg& m : P.sends) MMG_NCCL(n.Send(vec + m.offset, (size_t)m.count, ncclFloat64, m.peer, (ncclComm_t)s.nccl_comm, s.stream));
-  for (const ExchangePlan::Msg& m : P.recvs) MMG_NCCL(n.Recv(vec + m.offset, (size_t)m.count, ncclFloat64, m.peer, (ncclComm_t)s.nccl_comm, s.stream));
-  MMG_NCCL(n.GroupEnd());
+  {
+    NcclGroup grp(n);
+    for (const ExchangePlan::Msg& m : P.sends) MMG_NCCL(n.Send(vec + m.offset, (size_t)m.count, ncclFloat64, m.peer, (ncclComm_t)s.nccl_comm, s.stream));
+    for (const ExchangePlan::Msg& m : P.recvs) MMG_NCCL(n.Recv(vec + m.offset, (size_t)m.count, ncclFloat64, m.peer, (ncclComm_t)s.nccl_comm, s.stream));
+    grp.close();
+  }
   s.comm_msgs += (int64_t)P.sends.size() + (int64_t)P.recvs.size();
   for (const ExchangePlan::Msg& m : P.sends) s.comm_bytes += (int64_t)m.count * 8;
 }
@@ -188,12 +215,14 @@ void plan_execute(Solver& s, const ExchangePlan& P, double* vec) {
 void allgather_blocks(Solver& s, double* vec, const std::vector<int>& bounds) {
   if (s.world == 1) return;
   NcclApi& n = nccl();
-  MMG_NCCL(n.GroupStart());
-  for (int r = 0; r < s.world; r++) {
-    const int cnt = bounds[r + 1] - bounds[r];
-    if (cnt > 0) MMG_NCCL(n.Broadcast(vec + bounds[r], vec + bounds[r], (size_t)cnt, ncclFloat64, r, (ncclComm_t)s.nccl_comm, s.stream));
+  {
+    NcclGroup grp(n);
+    for (int r = 0; r < s.world; r++) {
+      const int cnt = bounds[r + 1] - bounds[r];
+      if (cnt > 0) MMG_NCCL(n.Broadcast(vec + bounds[r], vec + bounds[r], (size_t)cnt, ncclFloat64, r, (ncclComm_t)s.nccl_comm, s.stream));
+    }
+    grp.close();
   }
-  MMG_NCCL(n.GroupEnd());
   s.comm_msgs += s.world;
   s.comm_bytes += (int64_t)(bounds[s.rank + 1] - bounds[s.rank]) * 8 * (s.world - 1);
 }

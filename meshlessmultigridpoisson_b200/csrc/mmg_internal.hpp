@@ -140,6 +140,7 @@ struct Timers {
 struct Grid {
   int device = 0;
   int level = 0;    // position inside the owning solver (0 = coarsest); only used to bucket the timers
+  void* owner = nullptr;   // the Solver that took ownership (Multigrid::addGrid, multigrid.cpp:10-16); guards double adds / frees
   int n = 0;        // laplaceMatSize_
   int A = 0;        // rows of laplaceMat_ (n, or n+1 with any Neumann boundary)
   bool neumann = false, implicit = false;
@@ -168,6 +169,7 @@ struct Grid {
   DevBuf<double> dir_vals, neu_vals;
   HybMatrix Lap;                         // laplaceMat_
   DevBuf<double> partials;               // reduction scratch
+  DevBuf<double> reg_prod;               // products of the regularisation row (reference-order dot product, two stages)
   DevBuf<int> abort_flag;
   // multicolour schedule
   bool have_colours = false;
@@ -181,12 +183,10 @@ struct Grid {
   std::vector<int> mc_colour_ptr;        // colour offsets inside the packed copy
   DevBuf<int> mc_colour_ptr_dev;
   bool mc_packed = false;
+  int mc_bnd_phase = -1;                 // Neumann-type grid: index (inside a sweep) of the boundary-evaluation / regularisation phase of the packed copy
+  DevBuf<double> mc_reg_partial;         // per sweep and CTA: partial dot products of the regularisation row
   DevBuf<int> mc_ctl;                    // tile tickets + colour-barrier arrival counters of the TMA-fed sweep (zeroed per launch)
   DevBuf<unsigned char> mc_chunks;       // colour-major packed copy of Lap.chunks (Morton order inside a colour), fast multicolour sweep
-  int mc_regions = 0;                    // > 0: mc_chunks is region-major (k_sor_mc_regions), one region per co-resident CTA
-  DevBuf<int> mc_blk_ptr, mc_nbr_ptr, mc_nbr;   // (region, colour) block offsets; adjacency lists of the regions
-  DevBuf<unsigned> mc_done;              // finished phases per region, monotone across launches
-  unsigned mc_epoch = 0;
   // block-lexicographic schedule
   int block_size = 4096;
   bool have_blocks = false;

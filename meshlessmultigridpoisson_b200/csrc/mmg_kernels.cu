@@ -140,91 +140,8 @@ __global__ void __launch_bounds__(kBlock) k_finish_sor_reg(const double* __restr
 // row always has a running owner whose dependencies are done: no deadlock.  A clock64 watchdog
 // turns any stall into MMG_ERR_TIMEOUT instead of a hung GPU.
 // ------------------------------------------------------------------------------------------------
-template <int LPR, int T>
-__global__ void __launch_bounds__(kBlock) k_sor_lex(HybView A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b,
-                                                    const double* __restrict__ x_old, double* x_new, double omega, int* abort_flag,
-                                                    long long timeout_cycles) {
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % LPR;
-  const unsigned gmask = group_mask<LPR>(lane);
-  constexpr int GPW = 32 / LPR;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const long long t_start = clock64();
-  for (int row0 = warp * GPW; row0 < A.rows; row0 += nwarps * GPW) {
-    const int row = row0 + lane / LPR;
-    const bool valid = row < A.rows && rowflag[row] == 0;
-    double acc = 0.0, diag = 0.0;
-    double pv[T];
-    int pc[T];
-    unsigned pend = 0;
-    if (valid) {
-      const int len = A.len[row];
-      const double* __restrict__ v = row_val(A, row);
-      const int* __restrict__ c = row_col(A, row);
-      const int m = len < A.W ? len : A.W;
-#pragma unroll
-      for (int t = 0; t < T; t++) {
-        const int k = gl + t * LPR;
-        pv[t] = 0.0; pc[t] = 0;
-        if (k < m) {
-          const double a = v[k];
-          const int col = c[k];
-          if (k == 0) diag = a;                                   // diag-first layout
-          else if (col > row) acc = __dsub_rn(acc, __dmul_rn(a, __ldg(x_old + col)));
-          else { pv[t] = a; pc[t] = col; pend |= 1u << t; }
-        }
-      }
-      if (len > A.W) {  // rare spill rows (implicit Neumann fill-in): blocking per-entry wait
-        const int o = ovf_find(A, row);
-        for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) {
-          const int col = A.ovf_col[k];
-          double xv;
-          if (col > row) xv = __ldg(x_old + col);
-          else {
-            xv = ld_relaxed(x_new + col);
-            while (is_sentinel(xv)) {
-              if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); xv = 0.0; break; }
-              xv = ld_relaxed(x_new + col);
-            }
-          }
-          acc = __dsub_rn(acc, __dmul_rn(A.ovf_val[k], xv));
-        }
-      }
-    }
-    bool finished = !valid;
-    unsigned spins = 0;
-    while (true) {
-#pragma unroll
-      for (int t = 0; t < T; t++) {
-        if (pend & (1u << t)) {
-          const double xv = ld_relaxed(x_new + pc[t]);
-          if (!is_sentinel(xv)) { acc = __dsub_rn(acc, __dmul_rn(pv[t], xv)); pend &= ~(1u << t); }
-        }
-      }
-      const unsigned ball = __ballot_sync(0xffffffffu, pend != 0);
-      if (!finished && (ball & gmask) == 0) {
-        const double s = group_sum<LPR>(acc, gmask);
-        if (gl == 0) {                                          // x=sum; x+=b; x*=w/d; x+=(1-w)x_old (grid.cpp:137-141)
-          double xi = __dadd_rn(s, b[row]);
-          xi = __dmul_rn(xi, omega / diag);
-          xi = __dadd_rn(xi, __dmul_rn(1 - omega, x_old[row]));
-          st_relaxed(x_new + row, xi);
-        }
-        finished = true;
-      }
-      if (__all_sync(0xffffffffu, finished)) break;
-      if ((++spins & 0xff) == 0) {
-        if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) {
-          atomicExch(abort_flag, 1);
-          if (!finished && gl == 0) st_relaxed(x_new + row, 0.0);  // unblock everyone behind us
-          return;
-        }
-      }
-    }
-  }
-}
-
+// (k_sor_lex_exact below is the kernel; a first-generation variant with reordered group sums was removed in round 2: it
+// deadlocked on Neumann-type grids beyond ~200k rows and was never the default.)
 __global__ void __launch_bounds__(kBlock) k_sweep_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x_old, double* x_new,
                                                        int rows, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -412,17 +329,48 @@ __global__ void __launch_bounds__(kBlock) k_spmv_exact(HybView A, int diag_first
   }
 }
 
-// regularisation row, sequential: partial[0] = sum_j val[j]*x[col[j]] in ascending column order (one warp)
-__global__ void __launch_bounds__(32) k_regdot_exact(const int* __restrict__ col, const double* __restrict__ val, int len, const double* x, double* partial) {
+// Regularisation row in the reference's summation order: partial[0] = sum_j val[j]*x[col[j]], ascending columns, ONE running
+// sum (grid.cpp:126-136 applied to the dense row of :570-576).  The N-term serial DADD chain cannot be parallelised without
+// changing the rounding, so the work around it is: (1) k_regdot_products forms every product in parallel (coalesced, the
+// gather of x included) into a scratch vector; (2) one warp streams that vector through a shared-memory ring (128-bit loads,
+// four 2 KB blocks in flight) and lane 0 runs the chain at the DADD latency.  First version (load -> gather -> 32 shuffles
+// per 32 terms) took 36 ms per 1M terms; this one is bounded by ~8 cycles per term.
+__global__ void __launch_bounds__(kBlock) k_regdot_products(const int* __restrict__ col, const double* __restrict__ val, int len, const double* x,
+                                                            double* __restrict__ prod) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) prod[j] = __dmul_rn(val[j], x[col[j]]);
+}
+__global__ void __launch_bounds__(32) k_regdot_exact(const double* __restrict__ prod, int len, double* partial) {
+  constexpr int BLK = 256, NBUF = 4;                    // doubles per block, blocks in flight
+  __shared__ __align__(16) double buf[NBUF][BLK];
   const int lane = threadIdx.x;
-  double s = 0.0;
-  for (int base = 0; base < len; base += 32) {
-    const int j = base + lane;
-    const double p = j < len ? __dmul_rn(val[j], x[col[j]]) : 0.0;
-    const int cnt = min(32, len - base);
+  const int nblk = (len + BLK - 1) / BLK;
+  auto issue = [&](int blk) {
+    double* dst = buf[blk % NBUF];
+    const int base = blk * BLK;
 #pragma unroll
-    for (int l = 0; l < 32; l++)
-      if (l < cnt) s = __dadd_rn(s, __shfl_sync(0xffffffffu, p, l));
+    for (int i = 0; i < BLK / 64; i++) {                // 32 lanes x 16 bytes x 4 = 2 KB
+      const int e = base + (i * 32 + lane) * 2;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (i * 32 + lane) * 2);
+      if (e + 1 < len) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(prod + e) : "memory");
+      else { dst[(i * 32 + lane) * 2] = e < len ? prod[e] : 0.0; dst[(i * 32 + lane) * 2 + 1] = 0.0; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int b = 0; b < NBUF - 1 && b < nblk; b++) issue(b);
+  double s = 0.0;
+  for (int blk = 0; blk < nblk; blk++) {
+    if (blk + NBUF - 1 < nblk) issue(blk + NBUF - 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(NBUF - 1) : "memory");
+    __syncwarp();
+    if (lane == 0) {
+      const double2* q = reinterpret_cast<const double2*>(buf[blk % NBUF]);
+      const int cnt = min(BLK, len - blk * BLK);        // absent entries are +0.0: s + 0.0 == s for every s except -0.0, which a sum starting at +0.0 never holds
+#pragma unroll 8
+      for (int i = 0; i < BLK / 2; i++) {
+        if (2 * i < cnt) { const double2 v = q[i]; s = __dadd_rn(s, v.x); s = __dadd_rn(s, v.y); }
+      }
+    }
+    __syncwarp();
   }
   if (lane == 0) partial[0] = s;
 }
@@ -1005,126 +953,16 @@ __device__ __forceinline__ double row_overflow(const HybView& A, int row, int le
   return acc;
 }
 
-// ------------------------------------------------------------------------------------------------
-// x-tile staging (third generation).  ncu on the second-generation kernels shows the gathers, not the matrix
-// stream, holding them back: a warp-wide gather of 32 scattered doubles costs up to 32 L1 wavefronts and pulls a
-// 32-byte L2 sector per 8 useful bytes (profiles/r01_sor_mc2_4M_ncu.txt: L1 hit 23 %, DRAM 1.6x the algorithmic
-// bytes).  In the reference's BFS ordering the columns a CTA's rows touch fall into a few short index ranges (arcs of
-// three neighbouring BFS rings), so each CTA (a) loads its rows' chunks, (b) marks the 64-entry blocks of x those
-// columns touch, (c) copies the touched blocks into shared memory with coalesced loads, (d) gathers from shared
-// memory (bank conflicts instead of wavefronts).  No precomputed schedule: the block map is rebuilt per tile.
-// ------------------------------------------------------------------------------------------------
-constexpr int kStageBlk = 64;          // entries per staged block
-constexpr int kStageMap = 2048;        // blocks covered by the map: 131072 columns from the tile's smallest column
-constexpr int kStageCap = 96;          // staged blocks per tile (48 KB of x)
-constexpr size_t kStageSmem = (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2 + kStageMap + kStageCap * 2 + 64;
-
-struct StageSmem {
-  double* xs;              // kStageCap * 64 staged values
-  unsigned short* blk2off; // per map block: staged slot or 0xFFFF
-  unsigned char* touched;  // per map block
-  unsigned short* list;    // staged slot -> map block
-  int* misc;               // [0] min column, [1] staged count, [2..9] warp scan scratch
-};
-__device__ __forceinline__ StageSmem stage_carve(unsigned char* raw) {
-  StageSmem S;
-  S.xs = reinterpret_cast<double*>(raw);
-  S.blk2off = reinterpret_cast<unsigned short*>(raw + (size_t)kStageCap * kStageBlk * 8);
-  S.touched = raw + (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2;
-  S.list = reinterpret_cast<unsigned short*>(raw + (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2 + kStageMap);
-  S.misc = reinterpret_cast<int*>(raw + (size_t)kStageCap * kStageBlk * 8 + kStageMap * 2 + kStageMap + kStageCap * 2);
-  return S;
-}
-
-// Build the tile's staged copy of x.  Every thread of the CTA calls this with the columns it holds (c[n], -1 = none).
-// Returns the base column of the map.  kBlock threads, 4 block barriers.
-template <int NC>
-__device__ __forceinline__ int stage_build(const StageSmem& S, const int (&c)[NC], const double* x, int xlen) {
-  const int tid = threadIdx.x;
-  if (tid == 0) S.misc[0] = 0x7fffffff;
-  for (int i = tid; i < kStageMap / 8; i += kBlock) reinterpret_cast<unsigned long long*>(S.touched)[i] = 0ull;
-  int mn = 0x7fffffff;
-#pragma unroll
-  for (int n = 0; n < NC; n++) if (c[n] >= 0) mn = min(mn, c[n]);
-  mn = __reduce_min_sync(0xffffffffu, mn);
-  __syncthreads();
-  if ((tid & 31) == 0 && mn != 0x7fffffff) atomicMin(&S.misc[0], mn);
-  __syncthreads();
-  const int cbase = S.misc[0] == 0x7fffffff ? 0 : (S.misc[0] & ~(kStageBlk - 1));
-#pragma unroll
-  for (int n = 0; n < NC; n++)
-    if (c[n] >= 0) { const int blk = (c[n] - cbase) / kStageBlk; if (blk < kStageMap) S.touched[blk] = 1; }
-  __syncthreads();
-  {  // exclusive scan of touched[]: 8 map blocks per thread
-    constexpr int PER = kStageMap / kBlock;
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < PER; j++) cnt += S.touched[tid * PER + j];
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
-    if ((tid & 31) == 31) S.misc[2 + (tid >> 5)] = incl;
-    __syncthreads();
-    int base = 0;
-    for (int w = 0; w < (tid >> 5); w++) base += S.misc[2 + w];
-    int run = base + incl - cnt;
-#pragma unroll
-    for (int j = 0; j < PER; j++) {
-      const int blk = tid * PER + j;
-      if (S.touched[blk]) {
-        if (run < kStageCap) { S.blk2off[blk] = (unsigned short)run; S.list[run] = (unsigned short)blk; }
-        else S.blk2off[blk] = 0xFFFF;
-        run++;
-      } else S.blk2off[blk] = 0xFFFF;
-    }
-    if (tid == kBlock - 1) S.misc[1] = min(run, kStageCap);
-  }
-  __syncthreads();
-  const int staged = S.misc[1];
-  for (int e = tid; e < staged * kStageBlk; e += kBlock) {
-    const int g = cbase + (int)S.list[e / kStageBlk] * kStageBlk + (e % kStageBlk);
-    S.xs[e] = g < xlen ? x[g] : 0.0;
-  }
-  __syncthreads();
-  return cbase;
-}
-__device__ __forceinline__ double stage_read(const StageSmem& S, int cbase, int col, const double* x) {
-  const int rel = col - cbase;
-  const int blk = rel / kStageBlk;
-  if (blk < kStageMap) {
-    const unsigned off = S.blk2off[blk];
-    if (off != 0xFFFFu) return S.xs[off * kStageBlk + (rel % kStageBlk)];
-  }
-  return x[col];
-}
-
-template <int LPR, int ITER, bool SUB, bool DIAG0>
-__device__ __forceinline__ double row_accumulate_staged(const RowRegs<LPR, ITER>& r, const StageSmem& S, int cbase, const double* x, int gl, double& diag) {
-  double acc = 0.0;
-#pragma unroll
-  for (int t = 0; t < ITER; t++) {
-    if (DIAG0 && t == 0 && gl == 0) { diag = r.v[0]; continue; }
-    if (r.c[t] >= 0) {
-      const double p = __dmul_rn(r.v[t], stage_read(S, cbase, r.c[t], x));
-      acc = SUB ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
-    }
-  }
-  return acc;
-}
-
-template <int LPR, int ITER, int ROWS, bool STAGE>
+template <int LPR, int ITER, int ROWS>
 __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, const double* __restrict__ b, double* y,
                                                   const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
                                                   double* __restrict__ partial, int xlen, int row0, int nrows) {
-  extern __shared__ __align__(16) unsigned char stage_raw[];
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const unsigned gmask = group_mask<LPR>(lane);
   constexpr int GPW = 32 / LPR;
   constexpr int TR = (kBlock / 32) * GPW * ROWS;       // rows per CTA tile
   const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
-  StageSmem S;
-  if (STAGE) S = stage_carve(stage_raw);
   double num = 0.0, den = 0.0;
   const int ntiles = (nrows + TR - 1) / TR;            // rows [row0, row0+nrows): the whole matrix, or this rank's block
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1139,19 +977,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, co
       row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
     }
     double dummy;
-    if (STAGE) {
-      int cols[ROWS * ITER];
 #pragma unroll
-      for (int h = 0; h < ROWS; h++)
-#pragma unroll
-        for (int t = 0; t < ITER; t++) cols[h * ITER + t] = r[h].c[t];
-      const int cbase = stage_build<ROWS * ITER>(S, cols, x, xlen);
-#pragma unroll
-      for (int h = 0; h < ROWS; h++) acc[h] = row_accumulate_staged<LPR, ITER, false, false>(r[h], S, cbase, x, gl, dummy);
-    } else {
-#pragma unroll
-      for (int h = 0; h < ROWS; h++) acc[h] = row_accumulate<LPR, ITER, false, false>(r[h], x, keep, gl, dummy);
-    }
+    for (int h = 0; h < ROWS; h++) acc[h] = row_accumulate<LPR, ITER, false, false>(r[h], x, keep, gl, dummy);
     if (A.n_ovf) {
 #pragma unroll
       for (int h = 0; h < ROWS; h++) if (valid[h]) acc[h] = row_overflow<LPR, false>(A, row[h], len[h], x, gl, acc[h]);
@@ -1188,17 +1015,15 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(HybView A, const double* x, co
   }
 }
 
-template <int LPR, int ITER, int ROWS, bool STAGE>
+template <int LPR, int ITER, int ROWS>
 __device__ __forceinline__ void mc_phase(const HybView& A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
-                                         double omega, unsigned char* stage_raw, int xlen) {
+                                         double omega) {
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const unsigned gmask = group_mask<LPR>(lane);
   constexpr int GPW = 32 / LPR;
   constexpr int TR = (kBlock / 32) * GPW * ROWS;
   const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
-  StageSmem S;
-  if (STAGE) S = stage_carve(stage_raw);
   const int ntiles = (count + TR - 1) / TR;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     RowRegs<LPR, ITER> r[ROWS];
@@ -1213,19 +1038,8 @@ __device__ __forceinline__ void mc_phase(const HybView& A, const int* __restrict
     }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) row_fetch<LPR, ITER>(A, row[h], valid[h], gl, stream, r[h], len[h]);
-    if (STAGE) {
-      int cols[ROWS * ITER];
 #pragma unroll
-      for (int h = 0; h < ROWS; h++)
-#pragma unroll
-        for (int t = 0; t < ITER; t++) cols[h * ITER + t] = r[h].c[t];
-      const int cbase = stage_build<ROWS * ITER>(S, cols, x, xlen);
-#pragma unroll
-      for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate_staged<LPR, ITER, true, true>(r[h], S, cbase, x, gl, diag[h]); }
-    } else {
-#pragma unroll
-      for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate<LPR, ITER, true, true>(r[h], x, keep, gl, diag[h]); }
-    }
+    for (int h = 0; h < ROWS; h++) { diag[h] = 0.0; acc[h] = row_accumulate<LPR, ITER, true, true>(r[h], x, keep, gl, diag[h]); }
     if (A.n_ovf) {
 #pragma unroll
       for (int h = 0; h < ROWS; h++) if (valid[h]) acc[h] = row_overflow<LPR, true>(A, row[h], len[h], x, gl, acc[h]);
@@ -1246,28 +1060,10 @@ __device__ __forceinline__ void mc_phase(const HybView& A, const int* __restrict
   }
 }
 
-template <int LPR, int ITER, int ROWS, bool STAGE>
+template <int LPR, int ITER, int ROWS>
 __global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __restrict__ rows_list, int count, const double* __restrict__ b, double* x,
                                                     double omega, int xlen) {
-  extern __shared__ __align__(16) unsigned char stage_raw[];
-  mc_phase<LPR, ITER, ROWS, STAGE>(A, rows_list, count, b, x, omega, stage_raw, xlen);
-}
-
-// All colours of all `iters` sweeps of a grid without Neumann rows in ONE cooperative launch, a grid-wide barrier
-// between colour phases.  On the coarse levels a colour phase is a few microseconds of work, so per-colour launches
-// were launch-gap bound (ncu launch list, profiles/r01_launches_mc_4M_summary.txt: the W=25 levels took 44 % of the
-// cycle in 2100 launches).
-template <int LPR, int ITER, int ROWS, bool STAGE>
-__global__ void __launch_bounds__(kBlock) k_sor_mc_all(HybView A, const int* __restrict__ rows_list, const int* __restrict__ colour_ptr, int ncolours,
-                                                       int iters, const double* __restrict__ b, double* x, double omega, int xlen) {
-  extern __shared__ __align__(16) unsigned char stage_raw[];
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  for (int it = 0; it < iters; it++)
-    for (int c = 0; c < ncolours; c++) {
-      const int first = colour_ptr[c], count = colour_ptr[c + 1] - first;
-      mc_phase<LPR, ITER, ROWS, STAGE>(A, rows_list + first, count, b, x, omega, stage_raw, xlen);
-      grid.sync();
-    }
+  mc_phase<LPR, ITER, ROWS>(A, rows_list, count, b, x, omega);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1389,6 +1185,15 @@ __global__ void k_mark_lower_colour(unsigned char* chunks, size_t chunk_bytes, i
     const int cn = colour[pc[k]];
     if (cn >= 0 && cn < own) pc[k] |= 0x80000000;
   }
+}
+
+// rows longer than the chunk width (implicit-Neumann fill-in) carry bit 30 in their diagonal column: the TMA-fed sweep then
+// fetches the tail from the overflow CSR
+__global__ void k_mark_overflow(unsigned char* chunks, size_t chunk_bytes, int W, int total, const int* __restrict__ len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int* pc = reinterpret_cast<int*>(chunks + (size_t)i * chunk_bytes + (size_t)W * 8);
+  if (len[pc[0] & 0x3fffffff] > W) pc[0] |= 0x40000000;
 }
 
 template <int LPR, int ITER, int ROWS, bool PEER>
@@ -1568,131 +1373,67 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sor_mc_small(const unsigne
   for (int i = threadIdx.x; i < xlen; i += kSmallThreads) x[i] = xs[i];
 }
 
-// ------------------------------------------------------------------------------------------------
-// Region-synchronised multicolour sweep (fifth generation).  After packing, a colour phase is ~5 us of streaming
-// followed by a grid-wide barrier whose cost (barrier + drain + refill, ~4.6 us per phase, 220 phases per call) is
-// of the same size.  The packed rows are therefore cut into S spatial regions (consecutive ranges of the Z-curve,
-// equal row counts), one per co-resident CTA, stored region-major / colour-minor.  CTA s owns region s for the whole
-// call and runs its colours in order; before phase p it only waits until the regions its stencils touch have
-// finished phase p-1 (done[s'] >= p).  Because the region adjacency is symmetric this keeps exactly the
-// multicolour semantics -- a row of colour c sees colours < c of this sweep and colours > c of the previous one --
-// so the result is bit-identical to the barrier version, while neighbouring CTAs drift by at most one phase and
-// nobody waits for the slowest CTA of the grid.  Cooperative launch guarantees co-residency; the CTA with the
-// fewest finished phases can always run, so the waits cannot deadlock; a clock64 watchdog turns a bug into
-// MMG_ERR_TIMEOUT instead of a hung GPU.
-// ------------------------------------------------------------------------------------------------
-__global__ void k_region_adjacency(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W, const int* __restrict__ row_region,
-                                   const int* __restrict__ node_region, int total, int S, unsigned* __restrict__ adj) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int s = row_region[i];
-  const int* pc = reinterpret_cast<const int*>(chunks + (size_t)i * chunk_bytes + (size_t)W * 8);
-  int last = s;
-  for (int k = 0; k < W; k++) {
-    const int t = node_region[pc[k] & 0x7fffffff];
-    if (t >= 0 && t != s && t != last) { atomicOr(&adj[(size_t)s * ((S + 31) / 32) + (t >> 5)], 1u << (t & 31)); last = t; }
+// Coarsest levels (<= kResidentMaxBytes of packed operator): the WHOLE operator is copied into shared memory once per call,
+// next to values_ and source_, so a colour phase costs a shared-memory round trip and a block barrier (~0.1 us) instead of an
+// L2 round trip (~1 us: k_sor_mc_small above can only keep one tile of prefetch in flight).  Same per-row arithmetic, same bits.
+constexpr size_t kResidentMaxBytes = 200 * 1024;
+
+template <int LPR, int ITER>
+__global__ void __launch_bounds__(kSmallThreads, 1) k_sor_mc_resident(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W, int total_rows,
+                                                                      const int* __restrict__ colour_ptr, int ncolours, int iters,
+                                                                      const double* __restrict__ b, double* __restrict__ x, double omega, int xlen) {
+  extern __shared__ __align__(16) double small_smem[];
+  double* xs = small_smem;
+  double* bs = small_smem + xlen;
+  unsigned char* mat = reinterpret_cast<unsigned char*>(small_smem + 2 * (size_t)xlen);
+  for (int i = threadIdx.x; i < xlen; i += kSmallThreads) { xs[i] = x[i]; bs[i] = b[i]; }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(chunks);
+    uint4* dst = reinterpret_cast<uint4*>(mat);
+    const size_t n16 = (size_t)total_rows * chunk_bytes / 16;
+    for (size_t i = threadIdx.x; i < n16; i += kSmallThreads) dst[i] = src[i];
   }
-}
-
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <int LPR, int ITER, int ROWS>
-__global__ void __launch_bounds__(kBlock) k_sor_mc_regions(const unsigned char* __restrict__ chunks, size_t chunk_bytes, int W,
-                                                           const int* __restrict__ blk_ptr, int ncolours, int iters,
-                                                           const int* __restrict__ nbr_ptr, const int* __restrict__ nbr, unsigned* done, unsigned epoch,
-                                                           const double* __restrict__ b, double* x, double omega, int* abort_flag,
-                                                           long long timeout_cycles) {
-  const int s = blockIdx.x;
-  const int n0 = nbr_ptr[s], nn = nbr_ptr[s + 1] - n0;
-  const long long t_start = clock64();
-  __shared__ int aborted;
-  if (threadIdx.x == 0) aborted = 0;
+  const int lane = threadIdx.x & 31, gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  constexpr int GPW = 32 / LPR;
+  constexpr int TR = (kSmallThreads / 32) * GPW;
+  const int slot = (threadIdx.x >> 5) * GPW + lane / LPR;
+  const double om1 = 1 - omega;
   __syncthreads();
-  unsigned p = epoch;
-  for (int it = 0; it < iters; it++)
-    for (int c = 0; c < ncolours; c++, p++) {
-      // every region whose nodes my stencils read (or whose stencils read mine) has finished the previous phase
-      for (int k = threadIdx.x; k < nn; k += kBlock) {
-        const unsigned* flag = done + nbr[n0 + k];
-        // relaxed polls (an acquire load per spin would invalidate the SM's L1 under the other CTAs' gathers), one fence after
-        while ((int)(ld_relaxed_u32(flag) - p) < 0) {
-          if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = 1; break; }
-        }
+  const int nphases = iters * ncolours;
+  for (int p = 0; p < nphases; p++) {
+    const int col = p % ncolours;
+    const int first = colour_ptr[col], count = colour_ptr[col + 1] - first;
+    for (int i = slot; i < count; i += TR) {            // warp-uniform trip count is not needed: no barrier inside
+      const double* pv = reinterpret_cast<const double*>(mat + (size_t)(first + i) * chunk_bytes);
+      const int* pc = reinterpret_cast<const int*>(pv + W);
+      double v[ITER], xv[ITER];
+      int c[ITER];
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        const int k = gl + t * LPR;
+        const bool ok = k < W;
+        v[t] = ok ? pv[k] : 0.0;
+        c[t] = ok ? (pc[k] & 0x3fffffff) : -1;
+        xv[t] = ok ? xs[c[t]] : 0.0;
       }
-      if (threadIdx.x < nn) __threadfence();
-      __syncthreads();
-      if (aborted) return;
-      const int first = blk_ptr[s * ncolours + c], count = blk_ptr[s * ncolours + c + 1] - first;
-      if (count > 0) {
-        const int lane = threadIdx.x & 31;
-        const int gl = lane % LPR;
-        const unsigned gmask = group_mask<LPR>(lane);
-        constexpr int GPW = 32 / LPR;
-        constexpr int TR = (kBlock / 32) * GPW * ROWS;
-        const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
-        const unsigned char* base = chunks + (size_t)first * chunk_bytes;
-        for (int t0 = 0; t0 < count; t0 += TR) {
-          double v[ROWS][ITER], xx[ROWS][ITER], bi[ROWS], acc[ROWS];
-          int cc[ROWS][ITER];
-          bool valid[ROWS];
+      double a = 0.0;
 #pragma unroll
-          for (int h = 0; h < ROWS; h++) {
-            const int i = t0 + (threadIdx.x >> 5) * GPW * ROWS + h * GPW + lane / LPR;
-            valid[h] = i < count;
-            const double* pv = reinterpret_cast<const double*>(base + (size_t)(valid[h] ? i : 0) * chunk_bytes);
-            const int* pc = reinterpret_cast<const int*>(pv + W);
-#pragma unroll
-            for (int t = 0; t < ITER; t++) {
-              const int k = gl + t * LPR;
-              const bool ok = valid[h] && k < W;
-              v[h][t] = ok ? ldg_stream_f64(pv + k, stream) : 0.0;
-              cc[h][t] = ok ? ldg_stream_s32(pc + k, stream) : -1;
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < ROWS; h++)
-#pragma unroll
-            for (int t = 0; t < ITER; t++) {
-              if (cc[h][t] != -1) cc[h][t] &= 0x7fffffff;
-              xx[h][t] = cc[h][t] >= 0 ? ldg_keep(x + cc[h][t], keep) : 0.0;
-            }
-#pragma unroll
-          for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && valid[h]) ? b[cc[h][0]] : 0.0;
-#pragma unroll
-          for (int h = 0; h < ROWS; h++) {
-            double a = 0.0;
-#pragma unroll
-            for (int t = 0; t < ITER; t++) {
-              if (t == 0 && gl == 0) continue;
-              a = __dsub_rn(a, __dmul_rn(v[h][t], xx[h][t]));
-            }
-            acc[h] = a;
-          }
-#pragma unroll
-          for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
-          if (gl == 0) {
-#pragma unroll
-            for (int h = 0; h < ROWS; h++) {
-              if (valid[h]) {
-                double xi = __dadd_rn(acc[h], bi[h]);
-                xi = __dmul_rn(xi, omega / v[h][0]);
-                xi = __dadd_rn(xi, __dmul_rn(1 - omega, xx[h][0]));
-                x[cc[h][0]] = xi;
-              }
-            }
-          }
-        }
+      for (int t = 0; t < ITER; t++) {
+        if (t == 0 && gl == 0) continue;
+        a = __dsub_rn(a, __dmul_rn(v[t], xv[t]));
       }
-      __syncthreads();                                  // every store of this phase has been issued by the CTA
-      if (threadIdx.x == 0) { __threadfence(); st_release_u32(done + s, p + 1); }
+      a = group_sum<LPR>(a, gmask);
+      if (gl == 0) {
+        double xi = __dadd_rn(a, bs[c[0]]);
+        xi = __dmul_rn(xi, omega / v[0]);
+        xi = __dadd_rn(xi, __dmul_rn(om1, xv[0]));
+        xs[c[0]] = xi;
+      }
     }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < xlen; i += kSmallThreads) x[i] = xs[i];
 }
 
 __global__ void k_scatter(const int* __restrict__ idx, const double* __restrict__ vals, int count, double* dst, int use_zero) {
@@ -1749,11 +1490,6 @@ bool dispatch_lpr_iter(int W, F&& f, int prefer_lpr = 0) {
 #undef MMG_CASE
   return false;
 }
-// MMG_FAST_STAGE=1 turns the shared-memory x-tile staging on.  Off by default: measured 3x SLOWER than the
-// second-generation L2 gathers (784 vs 2515 GB/s on the 4M-node sweep) — four block barriers and a 2048-entry map scan
-// per 64-row tile serialise the HBM latency of the chunk loads with the staging loads.  Kept as the starting point for
-// a precomputed-segment, double-buffered version.
-int fast_stage() { static int v = -2; if (v == -2) { const char* e = getenv("MMG_FAST_STAGE"); v = e ? atoi(e) : 0; } return v; }
 constexpr int kSpmvRows = MMG_FAST_ROWS;   // rows in flight per lane group: 4 is best for the streaming SpMV kernels (profiles/r01_kernel_rates.txt)
 constexpr int kMcRows = 2;                 // ... and 2 for the multicolour sweep, whose gathers do not coalesce
 int grid_for2(int rows, int lpr, int sm_count, int per = kSpmvRows) { return grid_for((rows + per - 1) / per, lpr, sm_count); }
@@ -1774,19 +1510,12 @@ void launch_spmv(const HybMatrix& M, const double* x, const double* b, double* y
   if (nrows >= env_int("MMG_SPMV_TMA_MIN_ROWS", 30000) && env_int("MMG_SPMV_TMA", 1) &&
       stream_spmv(M, x, b, y, rowflag, op, mask_d, mask_n, partial, nblocks_out, device, s, row0, nrows))
     return;
-  const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(M.W, [&](auto L, auto I) {
+  const bool done = dispatch_lpr_iter(M.W, [&](auto L, auto I) {
     constexpr int LPR = decltype(L)::value, ITER = decltype(I)::value;
     int blocks = grid_for2(nrows, LPR, sms);
     if (nblocks_out) *nblocks_out = blocks;
     note_kernel_slot(1, "k_spmv2", LPR, ITER, kSpmvRows);
-    if (fast_stage()) {
-      auto kern = k_spmv2<LPR, ITER, kSpmvRows, true>;
-      static bool configured = false;
-      if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem)); configured = true; }
-      kern<<<blocks, kBlock, kStageSmem, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols, row0, nrows);
-    } else {
-      k_spmv2<LPR, ITER, kSpmvRows, false><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols, row0, nrows);
-    }
+    k_spmv2<LPR, ITER, kSpmvRows><<<blocks, kBlock, 0, s>>>(M.view(), x, b, y, rowflag, op, mask_d, mask_n, partial, M.cols, row0, nrows);
   });
   MMG_REQUIRE(done || (row0 == 0 && nrows == M.rows), MMG_ERR_STATE, "row-block launch: stencil width outside the fast kernels' table");
   if (!done)
@@ -1959,7 +1688,10 @@ static int launch_regdot(Grid& g, const double* x, double* reg_partial) {
   const HybMatrix& L = g.Lap;
   if (L.reg_row < 0) return 0;
   if (g.exact) {
-    k_regdot_exact<<<1, 32, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, x, reg_partial);
+    if (g.reg_prod.n < (size_t)L.reg_len) g.reg_prod.alloc((size_t)L.reg_len);
+    k_regdot_products<<<std::max(1, std::min(kRegBlocks * 4, (L.reg_len + kBlock - 1) / kBlock)), kBlock, 0, g.stream>>>(L.reg_col.p, L.reg_val.p, L.reg_len, x,
+                                                                                                                     g.reg_prod.p);
+    k_regdot_exact<<<1, 32, 0, g.stream>>>(g.reg_prod.p, L.reg_len, reg_partial);
     MMG_CUDA(cudaGetLastError());
     return 1;
   }
@@ -2158,30 +1890,25 @@ static void launch_lex_kernel(Grid& g, K kernel, int LPR, const double* x_old, d
   void* args[] = {&A, &rf, &b, &x_old, &x_new, &omega, &abortp, &timeout};
   MMG_CUDA(cudaLaunchCooperativeKernel((void*)kernel, dim3(blocks), dim3(kBlock), args, 0, g.stream));
 }
-template <int LPR, int T>
-static void launch_lex(Grid& g, const double* x_old, double* x_new) { launch_lex_kernel(g, k_sor_lex<LPR, T>, LPR, x_old, x_new); }
 template <int T>
 static void launch_lex_exact(Grid& g, const double* x_old, double* x_new) { launch_lex_kernel(g, k_sor_lex_exact<T>, 32, x_old, x_new); }
 
 static void sor_lex_sweep(Grid& g) {
   const HybMatrix& L = g.Lap;
   const int W = L.W;
-  const int lpr = lanes_for_width(W);
-  const int T = (W + lpr - 1) / lpr;
   const double* x_old = g.x.p;
   double* x_new = g.x_alt.p;
   k_sweep_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, x_old, x_new, L.rows, g.A);
   MMG_CUDA(cudaGetLastError());
+  // The row kernel folds in the reference's column order in both arithmetic modes (a lexicographic sweep is latency bound, the
+  // in-order fold costs nothing extra); MMG_ARITH_FAST only replaces the in-order sum of the dense regularisation row -- one
+  // warp adding ~N terms one after the other -- by a tree reduction (launch_regdot).
   const int Te = (W - 1 + 31) / 32;
-#define LEXE_CASE(T_) if (g.exact && Te <= T_) { launch_lex_exact<T_>(g, x_old, x_new); } else
+#define LEXE_CASE(T_) if (Te <= T_) { launch_lex_exact<T_>(g, x_old, x_new); } else
   LEXE_CASE(1) LEXE_CASE(2) LEXE_CASE(3) LEXE_CASE(4) LEXE_CASE(6) LEXE_CASE(8)
-#undef LEXE_CASE
-#define LEX_CASE(LPR_, T_) if (!g.exact && lpr == LPR_ && T <= T_) { launch_lex<LPR_, T_>(g, x_old, x_new); } else
-  LEX_CASE(32, 1) LEX_CASE(32, 2) LEX_CASE(32, 3) LEX_CASE(32, 4) LEX_CASE(32, 6) LEX_CASE(32, 8)
-  LEX_CASE(16, 2) LEX_CASE(16, 3)
-  LEX_CASE(8, 1) LEX_CASE(8, 2) LEX_CASE(8, 3)
   { throw Error(MMG_ERR_ARG, "stencil width " + std::to_string(W) + " is outside the lexicographic kernel's dispatch table"); }
-#undef LEX_CASE
+#undef LEXE_CASE
+  note_kernel(g, "k_sor_lex_exact", Te);
   if (L.reg_row >= 0) {
     double* reg_partial = g.partials.p;
     const int n_reg = launch_regdot(g, x_new, reg_partial);
@@ -2284,20 +2011,13 @@ static void sor_mc_sweep(Grid& g) {
       k_sor_mc_exact<<<grid_for(count, 32, sms), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega);
     }
   } else {
-    const bool done = !getenv("MMG_FAST_GEN1") && dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+    const bool done = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
       constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
       for (int c = 0; c < ncol_rows; c++) {
         const int first = g.colour_ptr[c], count = g.colour_ptr[c + 1] - first;
         if (count == 0) continue;
-        const int blocks = grid_for2(count, LPR, sms, kMcRows);
-        if (fast_stage()) {
-          auto kern = k_sor_mc2<LPR, ITER, kMcRows, true>;
-          static bool configured = false;
-          if (!configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem)); configured = true; }
-          kern<<<blocks, kBlock, kStageSmem, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega, g.A);
-        } else {
-          k_sor_mc2<LPR, ITER, kMcRows, false><<<blocks, kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p, g.props.omega, g.A);
-        }
+        k_sor_mc2<LPR, ITER, kMcRows><<<grid_for2(count, LPR, sms, kMcRows), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p, g.x.p,
+                                                                                                   g.props.omega, g.A);
       }
     });
     if (!done)
@@ -2319,13 +2039,21 @@ static void sor_mc_sweep(Grid& g) {
   }
 }
 
+// launch one of the register-fed whole-call kernels (grid barrier / barrier-free) over the packed copy
+template <class Launch>
+static bool launch_packed_family(Grid& g, Launch&& launch) {
+  const HybMatrix& L = g.Lap;
+  return dispatch_lpr_iter(L.W, launch, (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0);   // 8 lanes per row on the big levels: 4 rows per gather instruction share lines (+5 %)
+}
+
 void op_sor(Grid& g, int smoother) {
   MMG_REQUIRE(g.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built or uploaded");
   const HybMatrix& L = g.Lap;
   ensure_partials(g, (size_t)kRegBlocks + 2 * (sm_count_of(g.device) * 32 + 8));
   if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.have_colours) build_colouring(g);
+  const int64_t call_bytes = (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters;
   if (smoother == MMG_SMOOTHER_LEXICOGRAPHIC && !g.neumann && g.Lap.n_ovf == 0 && g.props.iters >= 1 && g.Lap.W <= 257 && !env_int("MMG_LEX_NO_PIPE", 0)) {
-    TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 3);
+    TimedScope ts(g, MMG_T_SOR, call_bytes, 3);
     sor_lex_pipelined(g);
     return;
   }
@@ -2333,41 +2061,36 @@ void op_sor(Grid& g, int smoother) {
     MMG_REQUIRE(!g.neumann, MMG_ERR_STATE, "the block-lexicographic smoother is implemented for grids without Neumann boundaries");
     if (!g.have_blocks) build_block_colouring(g);
   }
-  if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && !g.neumann && L.n_ovf == 0 && L.diag_first && g.props.iters >= 1 &&
-      (int)g.hx.size() == g.n && g.mc_row1 < 0 && env_int("MMG_MC_PACKED", 1) && !env_int("MMG_MC_PER_COLOUR", 0)) {
+  // Throughput mode: every colour phase of every sweep of the call in ONE launch over the colour-major packed copy.
+  //   <= 512 rows              k_sor_mc_small   one CTA, vectors in shared memory
+  //   <= MMG_MC_FLOW_MAX_ROWS  k_sor_mc_flow    barrier-free, the values are the ready flags (latency-bound levels)
+  //   above, and every grid with a Neumann boundary: k_sor_mc_tma, the TMA-fed ring with one counter barrier per phase
+  //   (mmg_stream.cu); k_sor_mc_packed (register-fed, grid.sync) is the fallback when the stencil width has no instantiation.
+  if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && L.diag_first && g.props.iters >= 1 && (int)g.hx.size() == g.n && g.mc_row1 < 0 &&
+      env_int("MMG_MC_PACKED", 1)) {
     ensure_mc_pack(g);
-    if (g.mc_regions > 0) {
+    const bool plain = !g.neumann && L.n_ovf == 0;      // no regularisation row, no boundary evaluation, no overflow tails
+    const size_t resident_bytes = (size_t)g.mc_colour_ptr.back() * L.chunk_bytes + (size_t)g.A * 16;
+    if (plain && resident_bytes <= kResidentMaxBytes && env_int("MMG_MC_RESIDENT", 1)) {
       bool ok = false;
       {
-        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
+        TimedScope ts(g, MMG_T_SOR, call_bytes, 1);
         ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
           constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
-          void* kern = (void*)k_sor_mc_regions<LPR, ITER, kMcRows>;
-          const unsigned char* chunks = g.mc_chunks.p;
-          size_t cb = L.chunk_bytes;
-          int W = L.W;
-          const int* bp = g.mc_blk_ptr.p;
-          int nc = g.n_colours, iters = g.props.iters;
-          const int* np = g.mc_nbr_ptr.p;
-          const int* nb = g.mc_nbr.p;
-          unsigned* dn = g.mc_done.p;
-          unsigned epoch = g.mc_epoch;
-          const double* b = g.b.p;
-          double* x = g.x.p;
-          double omega = g.props.omega;
-          int* abortp = g.abort_flag.p;
-          long long timeout = 6000000000ll;
-          void* args[] = {&chunks, &cb, &W, &bp, &nc, &iters, &np, &nb, &dn, &epoch, &b, &x, &omega, &abortp, &timeout};
-          MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(g.mc_regions), dim3(kBlock), args, 0, g.stream));
-          g.mc_epoch += (unsigned)(nc * iters);
+          auto kern = k_sor_mc_resident<LPR, ITER>;
+          note_kernel(g, "k_sor_mc_resident", LPR, ITER);
+          MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResidentMaxBytes));
+          kern<<<1, kSmallThreads, resident_bytes, g.stream>>>(g.mc_chunks.p, L.chunk_bytes, L.W, g.mc_colour_ptr.back(), g.mc_colour_ptr_dev.p, g.n_colours,
+                                                                g.props.iters, g.b.p, g.x.p, g.props.omega, g.A);
+          MMG_CUDA(cudaGetLastError());
         });
       }
       if (ok) return;
     }
-    if (g.A <= std::min(kSmallMaxRows, env_int("MMG_MC_SMALL_MAX", kSmallMaxRows)) && env_int("MMG_MC_SMALL", 1)) {
+    if (plain && g.A <= std::min(kSmallMaxRows, env_int("MMG_MC_SMALL_MAX", kSmallMaxRows)) && env_int("MMG_MC_SMALL", 1)) {
       bool ok = false;
       {
-        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
+        TimedScope ts(g, MMG_T_SOR, call_bytes, 1);
         ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
           constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
           auto kern = k_sor_mc_small<LPR, ITER>;
@@ -2381,14 +2104,14 @@ void op_sor(Grid& g, int smoother) {
       }
       if (ok) return;
     }
-    if (g.mc_regions == 0 && g.A <= env_int("MMG_MC_FLOW_MAX_ROWS", 1500000) && env_int("MMG_MC_FLOW", 1)) {
+    if (plain && g.A <= env_int("MMG_MC_FLOW_MAX_ROWS", 1500000) && env_int("MMG_MC_FLOW", 1)) {
       bool ok = false;
       {
-        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 3);
+        TimedScope ts(g, MMG_T_SOR, call_bytes, 3);
         const int iters = g.props.iters;
         const size_t stride = ((size_t)g.A + 63) / 64 * 64;
         if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
-        ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+        ok = launch_packed_family(g, [&](auto Lc, auto I) {
           constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
           k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
           MMG_CUDA(cudaGetLastError());
@@ -2415,79 +2138,50 @@ void op_sor(Grid& g, int smoother) {
           void* args[] = {&chunks, &cb, &W, &cp, &nc, &itn, &b, &xs, &st, &omega, &abortp, &timeout, &peers};
           MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
           MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
-        }, (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0);
+        });
       }
       if (ok) return;
     }
-    if (env_int("MMG_MC_TMA", 1)) {       // default on the big levels: the TMA-fed ring (mmg_stream.cu)
+    if (env_int("MMG_MC_TMA", 1) || !plain) {
       bool ok = false;
       {
-        TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 2);
+        TimedScope ts(g, MMG_T_SOR, call_bytes, 2);
         ok = stream_sor_mc(g);
       }
       if (ok) return;
     }
-    bool done = false;
-    {
-      TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
-      const int rows_pref = env_int("MMG_MC_ROWS", 2);
-      done = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
-        constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
-        void* kern = rows_pref >= 4 ? (void*)k_sor_mc_packed<LPR, ITER, 4> : rows_pref == 1 ? (void*)k_sor_mc_packed<LPR, ITER, 1> : (void*)k_sor_mc_packed<LPR, ITER, 2>;
-        const int rows_used = rows_pref >= 4 ? 4 : rows_pref == 1 ? 1 : 2;
-        note_kernel(g, "k_sor_mc_packed", LPR, ITER, rows_used);
-        int blocks_per_sm = 0;
-        MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
-        const int sms = sm_count_of(g.device);
-        int maxcount = 0;
-        for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.mc_colour_ptr[c + 1] - g.mc_colour_ptr[c]);
-        int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, rows_used));
-        const unsigned char* chunks = g.mc_chunks.p;
-        size_t cb = L.chunk_bytes;
-        int W = L.W;
-        const int* cp = g.mc_colour_ptr_dev.p;
-        int nc = g.n_colours, iters = g.props.iters;
-        const double* b = g.b.p;
-        double* x = g.x.p;
-        double omega = g.props.omega;
-        void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega};
-        MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
-      }, (g.A >= 200000 && L.W > 16 && L.W <= 40) ? 8 : 0);   // 8 lanes per row on the big levels: 4 rows per gather instruction share lines (+5 %)
+    if (plain) {
+      bool done = false;
+      {
+        TimedScope ts(g, MMG_T_SOR, call_bytes, 1);
+        const int rows_pref = env_int("MMG_MC_ROWS", 2);
+        done = launch_packed_family(g, [&](auto Lc, auto I) {
+          constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+          void* kern = rows_pref >= 4 ? (void*)k_sor_mc_packed<LPR, ITER, 4> : rows_pref == 1 ? (void*)k_sor_mc_packed<LPR, ITER, 1> : (void*)k_sor_mc_packed<LPR, ITER, 2>;
+          const int rows_used = rows_pref >= 4 ? 4 : rows_pref == 1 ? 1 : 2;
+          note_kernel(g, "k_sor_mc_packed", LPR, ITER, rows_used);
+          int blocks_per_sm = 0;
+          MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, 0));
+          const int sms = sm_count_of(g.device);
+          int maxcount = 0;
+          for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.mc_colour_ptr[c + 1] - g.mc_colour_ptr[c]);
+          int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, rows_used));
+          const unsigned char* chunks = g.mc_chunks.p;
+          size_t cb = L.chunk_bytes;
+          int W = L.W;
+          const int* cp = g.mc_colour_ptr_dev.p;
+          int nc = g.n_colours, iters = g.props.iters;
+          const double* b = g.b.p;
+          double* x = g.x.p;
+          double omega = g.props.omega;
+          void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega};
+          MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, 0, g.stream));
+        });
+      }
+      if (done) return;
     }
-    if (done) return;
   }
-  if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.exact && !g.neumann && L.n_ovf == 0 && g.props.iters >= 1 && !env_int("MMG_MC_PER_COLOUR", 0)) {
-    bool done = false;
-    {
-      TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters, 1);
-      done = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
-        constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
-        if (g.colour_ptr_dev.n != g.colour_ptr.size()) g.colour_ptr_dev.upload(g.colour_ptr, g.stream);
-        const bool stage = fast_stage() != 0;
-        void* kern = stage ? (void*)k_sor_mc_all<LPR, ITER, kMcRows, true> : (void*)k_sor_mc_all<LPR, ITER, kMcRows, false>;
-        const size_t smem = stage ? kStageSmem : 0;
-        static bool configured = false;
-        if (stage && !configured) { MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem)); configured = true; }
-        int blocks_per_sm = 0;
-        MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, smem));
-        const int sms = sm_count_of(g.device);
-        int maxcount = 0;
-        for (int c = 0; c < g.n_colours; c++) maxcount = std::max(maxcount, g.colour_ptr[c + 1] - g.colour_ptr[c]);
-        int blocks = std::min(blocks_per_sm * sms, grid_for2(maxcount, LPR, sms, kMcRows));
-        HybView A = L.view();
-        const int* rl = g.colour_rows.p;
-        const int* cp = g.colour_ptr_dev.p;
-        int nc = g.n_colours, iters = g.props.iters;
-        const double* b = g.b.p;
-        double* x = g.x.p;
-        double omega = g.props.omega;
-        int xlen = g.A;
-        void* args[] = {&A, &rl, &cp, &nc, &iters, &b, &x, &omega, &xlen};
-        MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kBlock), args, smem, g.stream));
-      });
-    }
-    if (done) return;
-  }
+  // per-phase launches: the reference-order (parity) kernels, partitioned levels, and anything the fused paths do not cover
   for (int it = 0; it < g.props.iters; it++) {
     {
       const int launches = smoother == MMG_SMOOTHER_MULTICOLOUR ? g.n_colours + 1 : smoother == MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC ? 3 * g.n_blk_colours : 2 + (L.reg_row >= 0 ? 2 : 0);
@@ -2844,7 +2538,7 @@ void dist_sor(Solver& s, int level) {
       if (count > 0) {
         const bool ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
           constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
-          k_sor_mc2<LPR, ITER, kMcRows, false><<<grid_for2(count, LPR, sms, kMcRows), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p,
+          k_sor_mc2<LPR, ITER, kMcRows><<<grid_for2(count, LPR, sms, kMcRows), kBlock, 0, g.stream>>>(L.view(), g.colour_rows.p + first, count, g.b.p,
                                                                                                            g.x.p, g.props.omega, g.A);
         });
         MMG_REQUIRE(ok, MMG_ERR_STATE, "stencil width outside the fast kernels' table");
@@ -2939,96 +2633,28 @@ void build_colouring(Grid& g) {
   g.mc_chunks.release();
 }
 
-// Region-major packed copy + region adjacency for k_sor_mc_regions.  `rows` holds every coloured row, colour-major and
-// in Z-curve order inside a colour.  Returns false (caller falls back to the barrier kernel) when no region count
-// gives adjacency lists short enough to poll.
-static bool mc_build_regions(Grid& g, const std::vector<int>& rows) {
-  const int nc = g.n_colours, total = (int)rows.size();
-  int max_resident = 0;
-  const bool known = dispatch_lpr_iter(g.Lap.W, [&](auto Lc, auto I) {
-    constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
-    int per_sm = 0;
-    MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_mc_regions<LPR, ITER, kMcRows>, kBlock, 0));
-    max_resident = per_sm * sm_count_of(g.device);
-  });
-  if (!known || max_resident < 1) return false;
-  // Z-curve rank of every coloured row: merge the per-colour sorted lists by key
-  double x0 = g.hx[0], x1 = g.hx[0], y0 = g.hy[0], y1 = g.hy[0];
-  for (int i = 0; i < g.n; i++) { x0 = std::min(x0, g.hx[i]); x1 = std::max(x1, g.hx[i]); y0 = std::min(y0, g.hy[i]); y1 = std::max(y1, g.hy[i]); }
-  const double sx = x1 > x0 ? 65535.0 / (x1 - x0) : 0.0, sy = y1 > y0 ? 65535.0 / (y1 - y0) : 0.0;
-  auto spread = [](uint32_t v) {
-    v &= 0xFFFFu;
-    v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
-    return v;
-  };
-  std::vector<std::pair<uint32_t, int>> keyed(total);
-  for (int k = 0; k < total; k++) {
-    const int r = rows[k];
-    keyed[k] = {spread((uint32_t)((g.hx[r] - x0) * sx)) | (spread((uint32_t)((g.hy[r] - y0) * sy)) << 1), r};
-  }
-  std::sort(keyed.begin(), keyed.end());
-  const int rows_per_region = std::max(16, env_int("MMG_MC_REGION_ROWS", 48));
-  int S = std::min(max_resident, std::max(1, total / rows_per_region));
-  const int cap = env_int("MMG_MC_REGION_CAP", 0);
-  if (cap > 0) S = std::min(S, cap);
-  for (int attempt = 0; attempt < 6 && S >= 1; attempt++, S = std::max(1, S / 2)) {
-    std::vector<int> node_region(g.A, -1), blk(static_cast<size_t>(S) * nc + 1, 0);
-    for (int k = 0; k < total; k++) node_region[keyed[k].second] = (int)((long long)k * S / total);
-    for (int k = 0; k < total; k++) { const int r = keyed[k].second; blk[(size_t)node_region[r] * nc + g.colour_host[r] + 1]++; }
-    for (size_t q = 0; q + 1 < blk.size(); q++) blk[q + 1] += blk[q];
-    std::vector<int> order(total), row_region(total), cur(blk.begin(), blk.end() - 1);
-    for (int k = 0; k < total; k++) {                       // Z-curve order survives inside every (region, colour) block
-      const int r = keyed[k].second;
-      const int dst = cur[(size_t)node_region[r] * nc + g.colour_host[r]]++;
-      order[dst] = r; row_region[dst] = node_region[r];
-    }
-    DevBuf<int> drows, drr, dnr;
-    drows.upload(order, g.stream); drr.upload(row_region, g.stream); dnr.upload(node_region, g.stream);
-    g.mc_chunks.alloc((size_t)total * g.Lap.chunk_bytes);
-    const long long threads = (long long)total * 32;
-    k_pack_chunks<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, g.stream>>>(g.Lap.chunks.p, g.Lap.chunk_bytes, drows.p, total, g.mc_chunks.p);
-    MMG_CUDA(cudaGetLastError());
-    const int words = (S + 31) / 32;
-    DevBuf<unsigned> dadj;
-    dadj.alloc((size_t)S * words); dadj.zero(g.stream);
-    k_region_adjacency<<<(total + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, drr.p, dnr.p, total, S, dadj.p);
-    MMG_CUDA(cudaGetLastError());
-    std::vector<unsigned> adj = dadj.to_host(g.stream);
-    auto bit = [&](int a, int b2) { return (adj[(size_t)a * words + (b2 >> 5)] >> (b2 & 31)) & 1u; };
-    std::vector<int> nptr(S + 1, 0), nlist;
-    int longest = 0;
-    for (int a = 0; a < S; a++) {
-      for (int b2 = 0; b2 < S; b2++) if (b2 != a && (bit(a, b2) || bit(b2, a))) nlist.push_back(b2);
-      nptr[a + 1] = (int)nlist.size();
-      longest = std::max(longest, nptr[a + 1] - nptr[a]);
-    }
-    if (longest > kBlock && S > 1) continue;                // polls are spread over the CTA's threads: keep it to one round
-    if (nlist.empty()) nlist.push_back(0);
-    g.mc_blk_ptr.upload(blk, g.stream);
-    g.mc_nbr_ptr.upload(nptr, g.stream);
-    g.mc_nbr.upload(nlist, g.stream);
-    g.mc_done.alloc(S); g.mc_done.zero(g.stream);
-    g.mc_epoch = 0;
-    MMG_CUDA(cudaStreamSynchronize(g.stream));
-    g.mc_regions = S;
-    g.mc_packed = true;
-    return true;
-  }
-  return false;
-}
-
-// Colour-major packed copy of laplaceMat_ for k_sor_mc_packed: the rows of every colour in Morton (Z-curve) order of
-// their node coordinates, so that consecutive rows of a colour form compact 2-D patches.
 void ensure_mc_pack(Grid& g) {
   if (g.mc_packed) return;
   MMG_REQUIRE(g.have_colours, MMG_ERR_STATE, "ensure_mc_pack: colouring missing");
   // rows the copy covers: everything, or this rank's block of a partitioned level (mc_row0/mc_row1)
   const int r0 = g.mc_row1 < 0 ? 0 : g.mc_row0, r1 = g.mc_row1 < 0 ? g.A : g.mc_row1;
   std::vector<int> rows;
-  g.mc_colour_ptr.assign(g.n_colours + 1, 0);
-  for (int c = 0; c < g.n_colours; c++) {
+  // interior colours; the regularisation row (last colour of a Neumann-type grid) has no chunk: the TMA-fed sweep handles it as
+  // a reduction inside the extra phase that also evaluates the Neumann boundary rows (last range of the packed copy)
+  const int n_int = g.Lap.reg_row >= 0 ? g.n_colours - 1 : g.n_colours;
+  g.mc_colour_ptr.assign(n_int + 1, 0);
+  for (int c = 0; c < n_int; c++) {
     for (int k = g.colour_ptr[c]; k < g.colour_ptr[c + 1]; k++) { const int r = g.colour_rows_host[k]; if (r >= r0 && r < r1) rows.push_back(r); }
     g.mc_colour_ptr[c + 1] = (int)rows.size();
+  }
+  const int total_int = (int)rows.size();
+  g.mc_bnd_phase = -1;
+  if (g.neumann) {
+    MMG_REQUIRE(g.mc_row1 < 0, MMG_ERR_STATE, "partitioned levels with Neumann boundaries are not supported");
+    for (const Boundary& bd : g.boundaries)
+      if (bd.type == MMG_BC_NEUMANN) rows.insert(rows.end(), bd.pts.begin(), bd.pts.end());
+    g.mc_colour_ptr.push_back((int)rows.size());
+    g.mc_bnd_phase = n_int;
   }
   g.mc_colour_ptr_dev.upload(g.mc_colour_ptr, g.stream);
   const int total = (int)rows.size();
@@ -3042,7 +2668,7 @@ void ensure_mc_pack(Grid& g) {
       return v;
     };
     std::vector<std::pair<uint32_t, int>> keyed;
-    for (int c = 0; c < g.n_colours; c++) {
+    for (int c = 0; c < n_int; c++) {
       const int a = g.mc_colour_ptr[c], e = g.mc_colour_ptr[c + 1];
       keyed.clear();
       for (int k = a; k < e; k++) {
@@ -3054,8 +2680,6 @@ void ensure_mc_pack(Grid& g) {
       for (int k = a; k < e; k++) rows[k] = keyed[k - a].second;
     }
   }
-  g.mc_regions = 0;
-  if (env_int("MMG_MC_REGIONS", 0) && total > 0 && g.mc_row1 < 0 && mc_build_regions(g, rows)) return;
   DevBuf<int> drows;
   drows.upload(rows, g.stream);
   g.mc_chunks.alloc((size_t)total * g.Lap.chunk_bytes);
@@ -3065,8 +2689,12 @@ void ensure_mc_pack(Grid& g) {
     MMG_CUDA(cudaGetLastError());
     DevBuf<int> dcol;
     dcol.upload(g.colour_host, g.stream);
-    k_mark_lower_colour<<<(total + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, total, dcol.p);
+    k_mark_lower_colour<<<(total_int + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, total_int, dcol.p);
     MMG_CUDA(cudaGetLastError());
+    if (g.Lap.n_ovf) {
+      k_mark_overflow<<<(total + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, total, g.Lap.len.p);
+      MMG_CUDA(cudaGetLastError());
+    }
     MMG_CUDA(cudaStreamSynchronize(g.stream));
   }
   MMG_CUDA(cudaStreamSynchronize(g.stream));

@@ -94,23 +94,55 @@ __device__ __forceinline__ void tile_row_fetch(const unsigned char* tile, unsign
 }
 
 // ------------------------------------------------------------------------------------------------
-// Multicolour SOR, all colours of all sweeps of one smoothing call (Dirichlet-type grids: no regularisation row, no
-// overflow rows) over the colour-major packed copy of the operator.
+// Multicolour SOR, every phase of all sweeps of one smoothing call over the colour-major packed copy of the operator
+// (DESIGN.md section 3).  A sweep is `pps` phases: the interior colours and, on a grid with a Neumann boundary, one more
+// phase that (a) evaluates the Neumann boundary rows -- Grid::bound_eval_neumann, grid.cpp:73-103: they read interior values
+// and themselves only, so they are one more set of independent rows, stored as the last range of the packed copy -- and
+// (b) forms the dot product of the dense regularisation row (grid.cpp:566-576), the last "colour" of the sweep: every CTA
+// reduces a fixed slice into reg_partial[sweep][cta]; after that phase's barrier every CTA folds the partials in the same
+// fixed order and stores the same new value of the regularisation unknown.  No atomics on doubles: the result is
+// reproducible for a given grid size.  Rows longer than the chunk width (implicit-Neumann fill-in, grid.cpp:607-657) carry
+// bit 30 in their diagonal column and fetch their tail from the overflow CSR of the natural-order operator.
 // ctl[0 .. nphases) = tile tickets, ctl[nphases .. 2 nphases) = barrier arrivals, zeroed by the host before the launch.
 // Cooperative launch (the colour barrier spins), one producer warp + eight consumer warps per CTA.
 // ------------------------------------------------------------------------------------------------
+struct RegRow {            // regularisation row of a Neumann-type grid (reg_row < 0: none)
+  const int* col;
+  const double* val;
+  int len, row;
+  double diag;
+  double* partial;         // iters x gridDim.x
+};
+constexpr int kColMask = 0x3fffffff;   // bit 31: neighbour of a lower colour (k_sor_mc_flow), bit 30: the row has an overflow tail
+
+__device__ __forceinline__ void grid_arrive(int* arrivals, int p) {
+  consumer_sync();
+  if (threadIdx.x == 0) { __threadfence(); red_release_add(&arrivals[p], 1); }
+}
+__device__ __forceinline__ void grid_wait(const int* arrivals, int p, int* abort_flag, long long timeout_cycles) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire(&arrivals[p]) < (int)gridDim.x) {
+      // watchdog: never hang the device; the sweep is abandoned (results invalid) and the host raises MMG_ERR_TIMEOUT
+      if (*(volatile int*)abort_flag || clock64() - t0 > timeout_cycles) { atomicExch(abort_flag, 1); break; }
+    }
+  }
+  consumer_sync();
+}
+
 template <int LPR, int ITER, int ROWS>
 __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned char* __restrict__ chunks, unsigned chunk_bytes, int W,
-                                                               const int* __restrict__ colour_ptr, int ncolours, int iters,
+                                                               const int* __restrict__ phase_ptr, int pps, int bnd_phase, int iters,
                                                                const double* __restrict__ b, double* x, double omega, int* ctl, int stages,
-                                                               int dynamic, int* abort_flag, long long timeout_cycles,
-                                                               int debug_flags) {
+                                                               int dynamic, int* abort_flag, long long timeout_cycles, int debug_flags, HybView A,
+                                                               RegRow reg) {
   extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red_scratch[kConsumerWarps];
   constexpr int GPW = 32 / LPR;
   constexpr int TR = kConsumerWarps * GPW * ROWS;      // rows per tile
   const unsigned tile_bytes = TR * chunk_bytes;
   RingCtl* C = ring_setup(smem, stages, tile_bytes);
-  const int nphases = iters * ncolours;
+  const int nphases = iters * pps;
   int* tickets = ctl;
   int* arrivals = ctl + nphases;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,9 +157,9 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
     for (;;) {
       int t = ticket, first = 0, count = 0;
       while (phase < nphases) {                          // the ticket is stale once its phase has no tiles left
-        const int c = phase % ncolours;
-        first = colour_ptr[c];
-        count = colour_ptr[c + 1] - first;
+        const int c = phase % pps;
+        first = phase_ptr[c];
+        count = phase_ptr[c + 1] - first;
         if (t < (count + TR - 1) / TR) break;
         if (++phase < nphases) t = dynamic ? atomicAdd(&tickets[phase], 1) : (int)blockIdx.x;
       }
@@ -155,26 +187,57 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
   const double om1 = 1 - omega;
   int cur_phase = 0, s = 0;
   unsigned par = 0;
+  double reg_old = 0.0;
   for (;;) {
     mbar_wait(&C->full[s], par);
     const int ph = C->phase[s];
-    if (ph != cur_phase) {                               // colour barrier: every CTA has stored its rows of the phases before `ph`
-      consumer_sync();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        for (int p = cur_phase; p < ph && p < nphases; p++) red_release_add(&arrivals[p], 1);
-        if (ph < nphases && !(debug_flags & 1)) {
-          const long long t0 = clock64();
-          while (ld_acquire(&arrivals[ph - 1]) < (int)gridDim.x) {
-            // watchdog: never hang the device; the sweep is abandoned (results invalid) and the host raises MMG_ERR_TIMEOUT
-            if (*(volatile int*)abort_flag || clock64() - t0 > timeout_cycles) { atomicExch(abort_flag, 1); break; }
+    if (ph != cur_phase) {
+      // Colour barrier.  Walk the phases this CTA leaves behind (it may have had no tile in some of them): arrive on each; a
+      // boundary / regularisation phase additionally needs the interior colours of its sweep complete before the dot product
+      // and every partial written before the new value of the regularisation unknown is formed.
+      int waited = cur_phase - 1;                        // barrier cur_phase-1 was passed when this CTA entered cur_phase
+      for (int p = cur_phase; p < ph; p++) {
+        const bool is_b = bnd_phase >= 0 && (p % pps) == bnd_phase;
+        if (is_b && reg.row >= 0) {
+          if (waited < p - 1) { grid_wait(arrivals, p - 1, abort_flag, timeout_cycles); waited = p - 1; }
+          const int per = (reg.len + (int)gridDim.x - 1) / (int)gridDim.x;
+          const int lo = min(reg.len, (int)blockIdx.x * per), hi = min(reg.len, lo + per);
+          double sum = 0.0;
+          for (int k = lo + (int)threadIdx.x; k < hi; k += kConsumers) sum = __dadd_rn(sum, __dmul_rn(reg.val[k], x[reg.col[k]]));
+          for (int o = 16; o > 0; o >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+          if (lane == 0) red_scratch[warp] = sum;
+          consumer_sync();
+          if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kConsumerWarps; w++) t = __dadd_rn(t, red_scratch[w]);
+            reg.partial[(size_t)(p / pps) * gridDim.x + blockIdx.x] = t;
+            reg_old = x[reg.row];                        // read before anybody can store the new value (that happens after barrier p)
           }
         }
+        grid_arrive(arrivals, p);
+        if (is_b && reg.row >= 0) {
+          grid_wait(arrivals, p, abort_flag, timeout_cycles); waited = p;
+          if (warp == 0) {                               // same fold order in every CTA: the value stored is identical
+            double dot = 0.0;
+            const double* part = reg.partial + (size_t)(p / pps) * gridDim.x;
+            for (int i = lane; i < (int)gridDim.x; i += 32) dot = __dadd_rn(dot, ld_relaxed(part + i));
+            for (int o = 16; o > 0; o >>= 1) dot = __dadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, o));
+            if (lane == 0) {                             // SOR update of the regularisation row, the last row of the sweep (grid.cpp:117-143)
+              double xi = -dot;
+              xi = __dadd_rn(xi, b[reg.row]);
+              xi = __dmul_rn(xi, omega / reg.diag);
+              xi = __dadd_rn(xi, __dmul_rn(om1, reg_old));
+              x[reg.row] = xi;
+            }
+          }
+          consumer_sync();
+        }
       }
-      consumer_sync();
       if (ph >= nphases) return;
+      if (waited < ph - 1 && !(debug_flags & 1)) grid_wait(arrivals, ph - 1, abort_flag, timeout_cycles);
       cur_phase = ph;
     }
+    const bool bnd = bnd_phase >= 0 && (ph % pps) == bnd_phase;
     const int n = C->nrows[s];
     const unsigned char* tile = smem + (size_t)s * tile_bytes;
     double v[ROWS][ITER], xx[ROWS][ITER], bi[ROWS], acc[ROWS];
@@ -187,13 +250,16 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
     __syncwarp();
     if (lane == 0) mbar_arrive(&C->empty[s]);            // the chunks are in registers: the stage can be refilled
     if (++s == stages) { s = 0; par ^= 1u; }
+    int tail[ROWS];
 #pragma unroll
-    for (int h = 0; h < ROWS; h++)
+    for (int h = 0; h < ROWS; h++) {
+      tail[h] = (gl == 0 && c[h][0] != -1) ? (c[h][0] >> 30) & 1 : 0;
 #pragma unroll
       for (int t = 0; t < ITER; t++) {
-        if (c[h][t] != -1) c[h][t] &= 0x7fffffff;        // bit 31 marks "neighbour of a lower colour" for k_sor_mc_flow
-        xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + ((debug_flags & 2) ? (c[h][0] & 0x7fffffff) : c[h][t]), keep) : 0.0;
+        if (c[h][t] != -1) c[h][t] &= kColMask;
+        xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + ((debug_flags & 2) ? c[h][0] : c[h][t]), keep) : 0.0;
       }
+    }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && c[h][0] >= 0) ? b[c[h][0]] : 0.0;   // slot 0 is the diagonal: its column is the row
 #pragma unroll
@@ -206,6 +272,17 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
       }
       acc[h] = a;
     }
+    if (A.n_ovf) {                                       // Neumann-type grids only: tails of the few rows longer than the chunk
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) {
+        const int has = __shfl_sync(gmask, tail[h], (lane / LPR) * LPR);
+        if (has) {
+          const int row = __shfl_sync(gmask, c[h][0], (lane / LPR) * LPR);
+          const int o = ovf_find(A, row);
+          for (int k = A.ovf_ptr[o] + gl; k < A.ovf_ptr[o + 1]; k += LPR) acc[h] = __dsub_rn(acc[h], __dmul_rn(A.ovf_val[k], x[A.ovf_col[k]]));
+        }
+      }
+    }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
     if (gl == 0) {
@@ -213,8 +290,12 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
       for (int h = 0; h < ROWS; h++) {
         if (c[h][0] >= 0) {
           double xi = __dadd_rn(acc[h], bi[h]);
-          xi = __dmul_rn(xi, omega / v[h][0]);
-          xi = __dadd_rn(xi, __dmul_rn(om1, xx[h][0]));   // xx[h][0] on lane 0 is x[row] before the update
+          if (bnd) {
+            xi = xi / v[h][0];                           // x_c = (b_c - sum_{k != c} a_ck x_k) / a_cc, grid.cpp:96-100
+          } else {
+            xi = __dmul_rn(xi, omega / v[h][0]);
+            xi = __dadd_rn(xi, __dmul_rn(om1, xx[h][0])); // xx[h][0] on lane 0 is x[row] before the update
+          }
           x[c[h][0]] = xi;
         }
       }
@@ -417,14 +498,16 @@ bool stream_sor_mc(Grid& g) {
     MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kStreamThreads, rs.smem));
     MMG_REQUIRE(blocks_per_sm >= 1, MMG_ERR_CUDA, "k_sor_mc_tma does not fit an SM");
     const int blocks = std::min(blocks_per_sm, rs.ctas_per_sm) * sms;
-    const int nphases = g.n_colours * g.props.iters;
+    const int pps = (int)g.mc_colour_ptr.size() - 1;       // phases per sweep: interior colours (+ the boundary / regularisation phase)
+    const int nphases = pps * g.props.iters;
     if (g.mc_ctl.n < (size_t)2 * nphases) g.mc_ctl.alloc((size_t)2 * nphases);
     MMG_CUDA(cudaMemsetAsync(g.mc_ctl.p, 0, sizeof(int) * 2 * nphases, g.stream));
+    if (L.reg_row >= 0 && g.mc_reg_partial.n < (size_t)g.props.iters * blocks) g.mc_reg_partial.alloc((size_t)g.props.iters * blocks);
     const unsigned char* chunks = g.mc_chunks.p;
     unsigned cb = (unsigned)L.chunk_bytes;
     int W = L.W;
     const int* cp = g.mc_colour_ptr_dev.p;
-    int nc = g.n_colours, iters = g.props.iters;
+    int bnd_phase = g.mc_bnd_phase, iters = g.props.iters, ppsv = pps;
     const double* b = g.b.p;
     double* x = g.x.p;
     double omega = g.props.omega;
@@ -433,7 +516,9 @@ bool stream_sor_mc(Grid& g) {
     int* abortp = g.abort_flag.p;
     long long timeout = 4000000000ll;                    // ~2 s of SM clocks per colour barrier
     int debug_flags = env_int("MMG_TMA_DEBUG", 0);      // timing decomposition only (1: no colour barrier, 2: no gathers): results invalid
-    void* args[] = {&chunks, &cb, &W, &cp, &nc, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &debug_flags};
+    HybView A = L.view();
+    RegRow reg{L.reg_col.p, L.reg_val.p, L.reg_len, L.reg_row, L.reg_diag, g.mc_reg_partial.p};
+    void* args[] = {&chunks, &cb, &W, &cp, &ppsv, &bnd_phase, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &debug_flags, &A, &reg};
     note_kernel(g, "k_sor_mc_tma", LPR, ITER, rows_used);
     MMG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(blocks), dim3(kStreamThreads), args, rs.smem, g.stream));
   });

@@ -9,7 +9,7 @@ the way the reference does (x==0 || x==1 || y==0 || y==1).
 import numpy as np
 
 from . import capi
-from .clouds import jittered_square
+from .clouds import jittered_square, make_cloud
 
 PI = 3.141592653589793238462643383279        # testing_functions.hpp:9
 
@@ -71,12 +71,12 @@ def make_grid(kind, x, y, poly_deg, k1=1, k2=1, fine=True, device=0, **props):
     return g
 
 
-def make_hierarchy(sizes, kind="dirichlet", fine_poly=4, coarse_poly=3, seed0=1000, jitter=0.3, device=0, **kw):
+def make_hierarchy(sizes, kind="dirichlet", fine_poly=4, coarse_poly=3, seed0=1000, jitter=0.3, device=0, cloud="jittered", **kw):
     """run_mg_sim's set-up (testing_functions.cpp:328-339) on synthetic clouds: one independent jittered lattice
     per level, coarse levels polyDeg 3, finest ``fine_poly``; then buildMatrices()."""
     mg = capi.Multigrid()
     for l, s in enumerate(sizes):
-        x, y = jittered_square(s, seed=seed0 + l, jitter=jitter)
+        x, y = make_cloud(cloud, s, seed0 + l, jitter)
         last = l == len(sizes) - 1
         mg.addGrid(make_grid(kind, x, y, fine_poly if last else coarse_poly, fine=last, device=device, **kw))
     mg.buildMatrices()

@@ -367,14 +367,14 @@ class Multigrid:
         return out[:n]
 
 
-def make_hierarchy(sizes, kind=KIND_DIRICHLET, fine_poly=4, coarse_poly=3, fracstep=False, cells=True, seed0=1000, jitter=0.3, **kw):
+def make_hierarchy(sizes, kind=KIND_DIRICHLET, fine_poly=4, coarse_poly=3, fracstep=False, cells=True, seed0=1000, jitter=0.3, cloud="jittered", **kw):
     """The reference's run_mg_sim set-up (testing_functions.cpp:328-339) on synthetic jittered
     lattices: one independent cloud per level, coarse levels polyDeg 3, finest fine_poly."""
-    from meshlessmultigridpoisson_b200.clouds import jittered_square
+    from meshlessmultigridpoisson_b200.clouds import make_cloud
 
     mg = Multigrid(fracstep=fracstep)
     for l, s in enumerate(sizes):
-        x, y = jittered_square(s, seed=seed0 + l, jitter=jitter)
+        x, y = make_cloud(cloud, s, seed0 + l, jitter)
         last = l == len(sizes) - 1
         mg.add_level(kind, x, y, fine_poly if last else coarse_poly, fine=last, cells=cells, **kw)
     mg.build()

@@ -65,3 +65,25 @@ def test_cpp_fracstep_driver_matches_python_driver_bit_for_bit(libmmg, tmp_path)
         assert n == cycles[k] and abs(r - old) == deltas[k]
         old = r
     assert 0 < cycles[0] < 200 and float(out[3].split()[1]) < 0.5
+
+
+def test_ownership_rules_of_add_grid(libmmg):
+    """Multigrid owns its grids (multigrid.cpp:10-16): a grid cannot be added twice, and the C-ABI refuses to destroy a grid a
+    solver owns (double free); wrappers returned by Multigrid.grid() keep their solver alive."""
+    import ctypes as C
+    import numpy as np
+    from meshlessmultigridpoisson_b200 import capi
+    from meshlessmultigridpoisson_b200.clouds import jittered_square
+    from meshlessmultigridpoisson_b200.problems import make_grid, make_hierarchy
+
+    x, y = jittered_square(13, 1)
+    g = make_grid("dirichlet", x, y, 3)
+    mg = capi.Multigrid()
+    mg.addGrid(g)
+    with pytest.raises(capi.MmgError) as e:
+        mg.addGrid(g)
+    assert e.value.code == capi.ERR_STATE
+    assert mg.L.mmg_grid_destroy(g.h) == capi.ERR_STATE
+    w = make_hierarchy([13, 25], "dirichlet", 3).grid(-1)      # the solver object is unreachable except through the wrapper
+    import gc; gc.collect()
+    assert np.isfinite(w.values_).all() and w.getSize() == 625

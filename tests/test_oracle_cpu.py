@@ -387,3 +387,24 @@ def test_error_convention_of_the_c_abi():
     assert L.mmg_partition_bounds(2, 3, b) == 0 and b.tolist() == [0, 1, 2, 2]        # more ranks than rows: empty trailing blocks
     info = C.c_char_p(L.mmg_build_info()).value if L.mmg_build_info.restype is not C.c_char_p else L.mmg_build_info()
     assert b"sm_100a" in info
+
+
+def test_missing_nccl_is_an_error_code_not_a_crash():
+    """libnccl is resolved with dlopen at first use; when it cannot be loaded the call must return MMG_ERR_NCCL with a message
+    (the error path used to read dlerror() twice and build a std::string from NULL)."""
+    import subprocess, sys, textwrap
+
+    code = textwrap.dedent("""
+        import ctypes, sys
+        sys.path.insert(0, %r)
+        from meshlessmultigridpoisson_b200 import capi
+        L = capi.load()
+        buf = ctypes.create_string_buffer(128)
+        rc = L.mmg_comm_unique_id(buf)
+        print(rc, L.mmg_last_error().decode())
+    """ % ROOT)
+    env = dict(os.environ, MMG_NCCL_LIB="/nonexistent/libnccl.so.2")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-1000:]
+    rc, msg = out.stdout.strip().split(" ", 1)
+    assert int(rc) == 4 and "cannot load libnccl" in msg          # MMG_ERR_NCCL
