@@ -40,6 +40,7 @@ typedef struct mmg_props {
 
 enum { MMG_OK = 0, MMG_ERR_ARG = 1, MMG_ERR_CUDA = 2, MMG_ERR_STATE = 3, MMG_ERR_NCCL = 4, MMG_ERR_TIMEOUT = 5 };
 enum { MMG_BC_DIRICHLET = 1, MMG_BC_NEUMANN = 2 };                  /* Boundary::type, grid.cpp:35 */
+enum { MMG_GEOM_SQUARE = 0, MMG_GEOM_SQUARE_WITH_CIRCLE = 1, MMG_GEOM_CONCENTRIC_CIRCLES = 2 };  /* the geomtype strings, testing_functions.cpp:81,92,107 */
 enum { MMG_FINE = 0, MMG_COARSE = 1 };                              /* the "fine"/"coarse" strings, grid.cpp:47,67 */
 enum { MMG_SMOOTHER_LEXICOGRAPHIC = 0, MMG_SMOOTHER_MULTICOLOUR = 1, MMG_SMOOTHER_BLOCK_LEXICOGRAPHIC = 2 };
 enum { MMG_FLAVOUR_MULTIGRID = 0, MMG_FLAVOUR_FRACSTEP = 1 };
@@ -69,6 +70,7 @@ int mmg_grid_destroy(mmg_grid* g);                                              
 int mmg_grid_set_implicit(mmg_grid* g, int flag);                                  /* Grid::implicitFlag_ grid.h:38 */
 int mmg_grid_set_bc_flag(mmg_grid* g, int boundary, int type, const double* values, int n_values); /* Grid::setBCFlag grid.cpp:33-40 */
 int mmg_grid_build_normal_vecs_square(mmg_grid* g);                                /* Grid::build_normal_vecs(.., "square") grid.cpp:442-461 */
+int mmg_grid_build_normal_vecs(mmg_grid* g, int geomtype);                          /* Grid::build_normal_vecs(.., geomtype) grid.cpp:442-516, MMG_GEOM_* */
 int mmg_grid_set_normal_vecs(mmg_grid* g, const double* nx, const double* ny);     /* Grid::normalVecs_ grid.h:28 (other geometries) */
 int mmg_grid_rcm_order_points(mmg_grid* g);                                        /* Grid::rcm_order_points grid.cpp:713-776 */
 int mmg_grid_build_deriv_normal_bound(mmg_grid* g);                                /* Grid::build_deriv_normal_bound grid.cpp:520-548 */
@@ -110,6 +112,9 @@ int mmg_grid_get_csr(mmg_grid* g, int which, int* ptr, int* idx, double* val);
 int mmg_grid_set_laplacian_csr(mmg_grid* g, int rows, const int* ptr, const int* idx, const double* val, const double* diags,
                                const int* nb_ptr, const int* nb_idx, const double* nb_val);
 /* integer artefacts of the GPU schedules (bit-exact against the oracle) */
+/* y = M x on the device, host vectors in and out (M one of MMG_MAT_LAPLACE / DERIVX / DERIVY / UVLAPLACE): the products the reference's
+ * drivers form with laplaceMat_, derivXMat_, derivYMat_, uvLaplaceMat_ (FractionalStepSim.cpp:80-113) */
+int mmg_grid_apply_matrix(mmg_grid* g, int which, const double* x, double* y);
 int mmg_grid_get_colouring(mmg_grid* g, int* n_colours, int* colour);              /* per row, -1 for rows the sweep skips */
 int mmg_grid_get_colour_counts(mmg_grid* g, int* n_colours, int* counts, int cap);  /* rows per colour class (one multicolour launch each) */
 int mmg_grid_set_block_size(mmg_grid* g, int rows_per_block);                      /* block-lexicographic smoother: rows per block (default 4096) */
@@ -182,6 +187,12 @@ int mmg_solver_comm_stats(mmg_solver* s, int64_t* messages, int64_t* bytes_sent,
 /* After a partitioned vcycle / solve, mmg_grid_get_values on a rank is current on that rank's row block and halo ranges only.
  * This collective completes values_ of every partitioned level on every rank (call it before reading the whole solution). */
 int mmg_solver_gather_values(mmg_solver* s);
+/* rows [own_lo, own_hi) of `level` belong to this rank; its kernels read values_ in [need_lo, need_hi) (row block + halo).
+ * With the ranged copies below a rank moves only that part of Grid::values_ / source_ between host and device. */
+int mmg_solver_owned_range(mmg_solver* s, int level, int* own_lo, int* own_hi, int* need_lo, int* need_hi);
+int mmg_grid_get_values_range(mmg_grid* g, int offset, int count, double* out);   /* values_[offset, offset+count) */
+int mmg_grid_set_values_range(mmg_grid* g, int offset, int count, const double* in);
+int mmg_grid_set_source_range(mmg_grid* g, int offset, int count, const double* in); /* source_[offset, offset+count) */
 
 /* ---------------------------------------------------------------- diagnostics (no reference counterpart) ---
  * Used by the test-suite to prove which kernel instantiation ran and to check host-side schedules. */

@@ -23,6 +23,7 @@ ARITH_REFERENCE_ORDER, ARITH_FAST = 0, 1
 MAT_LAPLACE, MAT_NEUMANN_COEFFS, MAT_RESTRICT, MAT_PROLONG, MAT_DERIVX, MAT_DERIVY, MAT_UVLAPLACE = range(7)
 T_SOR, T_RESIDUAL, T_RESTRICT, T_PROLONG, T_OTHER, T_COUNT = range(6)
 FS_U, FS_V, FS_U_OLD, FS_V_OLD, FS_U_HAT, FS_V_HAT = range(6)
+GEOMTYPES = ["square", "square_with_circle", "concentric_circles"]     # MMG_GEOM_*
 
 
 class MmgProps(C.Structure):
@@ -50,6 +51,7 @@ SIGNATURES = {
     "mmg_grid_set_implicit": [_vp, _i],
     "mmg_grid_set_bc_flag": [_vp, _i, _i, _vp, _i],
     "mmg_grid_build_normal_vecs_square": [_vp],
+    "mmg_grid_build_normal_vecs": [_vp, _i],
     "mmg_grid_set_normal_vecs": [_vp, _dp, _dp],
     "mmg_grid_rcm_order_points": [_vp],
     "mmg_grid_build_deriv_normal_bound": [_vp],
@@ -79,6 +81,7 @@ SIGNATURES = {
     "mmg_grid_get_boundary": [_vp, _i, C.POINTER(_i), C.POINTER(_i), _vp, _vp],
     "mmg_grid_csr_nnz": [_vp, _i, C.POINTER(C.c_int64)],
     "mmg_grid_get_csr": [_vp, _i, _ip, _ip, _dp],
+    "mmg_grid_apply_matrix": [_vp, _i, _dp, _dp],
     "mmg_grid_set_laplacian_csr": [_vp, _i, _ip, _ip, _dp, _vp, _vp, _vp, _vp],
     "mmg_grid_get_colouring": [_vp, C.POINTER(_i), _ip],
     "mmg_grid_get_lex_levels": [_vp, C.POINTER(_i), _ip],
@@ -130,6 +133,10 @@ SIGNATURES = {
     "mmg_solver_set_partition_threshold": [_vp, _i],
     "mmg_solver_comm_stats": [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_i)],
     "mmg_solver_gather_values": [_vp],
+    "mmg_solver_owned_range": [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
+    "mmg_grid_get_values_range": [_vp, _i, _i, _dp],
+    "mmg_grid_set_values_range": [_vp, _i, _i, _dp],
+    "mmg_grid_set_source_range": [_vp, _i, _i, _dp],
     "mmg_debug_last_kernel": [_i, C.c_char_p, _i],
     "mmg_debug_lex_trace": [_lp, _i],
     "mmg_debug_exchange_plan": [_i, _i, _ip, _ip, C.POINTER(_i), _ip, C.POINTER(_i), _ip],
@@ -244,6 +251,17 @@ class Grid:
         _ck(self.L, self.L.mmg_grid_get_values(self.h, out))
         return out
 
+    def read_values_range(self, offset, out):
+        """values_[offset, offset + out.size) into a caller-owned (pinned) buffer"""
+        _ck(self.L, self.L.mmg_grid_get_values_range(self.h, offset, out.size, out))
+        return out
+
+    def write_values_range(self, offset, v):
+        _ck(self.L, self.L.mmg_grid_set_values_range(self.h, offset, v.size, v))
+
+    def write_source_range(self, offset, v):
+        _ck(self.L, self.L.mmg_grid_set_source_range(self.h, offset, v.size, v))
+
     @values_.setter
     def values_(self, v):
         v = _f64(v)
@@ -314,8 +332,7 @@ class Grid:
         _ck(self.L, self.L.mmg_grid_set_implicit(self.h, int(flag)))
 
     def build_normal_vecs(self, geomtype="square"):
-        assert geomtype == "square"
-        _ck(self.L, self.L.mmg_grid_build_normal_vecs_square(self.h))
+        _ck(self.L, self.L.mmg_grid_build_normal_vecs(self.h, GEOMTYPES.index(geomtype)))
 
     def rcm_order_points(self):
         _ck(self.L, self.L.mmg_grid_rcm_order_points(self.h))
@@ -579,6 +596,14 @@ class Multigrid:
 
     def set_partition_threshold(self, rows):
         _ck(self.L, self.L.mmg_solver_set_partition_threshold(self.h, rows))
+
+    def owned_range(self, level=-1):
+        """(own_lo, own_hi, need_lo, need_hi) of this rank on `level` (whole vector when the level is not partitioned)"""
+        if level < 0:
+            level += self.num_grids
+        a, b, c, d = _i(), _i(), _i(), _i()
+        _ck(self.L, self.L.mmg_solver_owned_range(self.h, level, a, b, c, d))
+        return a.value, b.value, c.value, d.value
 
     def gather_values(self):
         """collective: complete values_ of every partitioned level on every rank (after a partitioned vCycle / solve)"""

@@ -49,10 +49,48 @@ def hex_square(s, seed=0, jitter=0.0, margin=0.3):
     return np.ascontiguousarray(np.concatenate([bx, P[:, 0]])), np.ascontiguousarray(np.concatenate([by, P[:, 1]]))
 
 
+def _circle(r, h):
+    n = max(8, int(round(2.0 * np.pi * r / h)))
+    t = 2.0 * np.pi * np.arange(n) / n
+    return 0.5 + r * np.cos(t), 0.5 + r * np.sin(t)
+
+
+def hole_square(s, seed, jitter=0.3, clearance=0.5):
+    """geomtype "square_with_circle" (testing_functions.cpp:92-106): jittered lattice on the unit square minus the disc of radius
+    0.25 about (0.5, 0.5), plus equispaced nodes on the circle.  The reference detects the circle by
+    |0.0625 - (x-0.5)^2 - (y-0.5)^2| <= 1e-10; nodes closer than ``clearance*h`` to it are dropped."""
+    h = 1.0 / (s - 1)
+    x, y = jittered_square(s, seed, jitter)
+    r = np.hypot(x - 0.5, y - 0.5)
+    keep = r > 0.25 + clearance * h
+    cx, cy = _circle(0.25, h)
+    return np.ascontiguousarray(np.concatenate([x[keep], cx])), np.ascontiguousarray(np.concatenate([y[keep], cy]))
+
+
+def annulus(s, seed, jitter=0.3, clearance=0.5):
+    """geomtype "concentric_circles" (testing_functions.cpp:107-135): nodes on the circles of radius 0.5 and 0.25 about (0.5, 0.5)
+    and a jittered lattice between them."""
+    h = 1.0 / (s - 1)
+    idx = np.arange(s, dtype=np.float64) / (s - 1)
+    x, y = np.meshgrid(idx, idx, indexing="xy")
+    rng = np.random.default_rng(seed)
+    x = (x + rng.uniform(-jitter * h, jitter * h, size=(s, s))).ravel()
+    y = (y + rng.uniform(-jitter * h, jitter * h, size=(s, s))).ravel()
+    r = np.hypot(x - 0.5, y - 0.5)
+    keep = (r > 0.25 + clearance * h) & (r < 0.5 - clearance * h)
+    ox, oy = _circle(0.5, h)
+    ix, iy = _circle(0.25, h)
+    return np.ascontiguousarray(np.concatenate([ox, ix, x[keep]])), np.ascontiguousarray(np.concatenate([oy, iy, y[keep]]))
+
+
 def make_cloud(kind, s, seed, jitter=0.3):
     """'jittered': SURVEY.md section 8d lattice; 'hex': the Gmsh-like cloud"""
     if kind == "hex":
         return hex_square(s, seed)
+    if kind == "square_with_circle":
+        return hole_square(s, seed, jitter)
+    if kind == "concentric_circles":
+        return annulus(s, seed, jitter)
     return jittered_square(s, seed=seed, jitter=jitter)
 
 

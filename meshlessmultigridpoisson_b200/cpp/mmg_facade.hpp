@@ -10,6 +10,7 @@
 // HostVector converts to and from Eigen::VectorXd.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <stdexcept>
 #include <fstream>
 #include <string>
@@ -58,9 +59,18 @@ class HostVector {
   HostVector& operator=(const HostVector& o) { if (this != &o) { if (g_) *this = o.host(); else { h_ = o.host(); } } return *this; }
   HostVector(const HostVector&) = delete;
   double lpNorm1() const { pull(); double s = 0; for (double t : h_) s += t < 0 ? -t : t; return s; }
+  template <int P> double lpNorm() const { static_assert(P == 1, "lpNorm<1> only (multigrid.cpp:114)"); return lpNorm1(); }
+  double maxCoeff() const { pull(); return *std::max_element(h_.begin(), h_.end()); }
+  double minCoeff() const { pull(); return *std::min_element(h_.begin(), h_.end()); }
 #ifdef MMG_FACADE_HAVE_EIGEN
-  operator Eigen::VectorXd() const { pull(); return Eigen::Map<const Eigen::VectorXd>(h_.data(), (Eigen::Index)h_.size()); }
-  HostVector& operator=(const Eigen::VectorXd& v) { h_.assign(v.data(), v.data() + v.size()); device_newer_ = false; host_newer_ = true; return *this; }
+  operator Eigen::VectorXd() const { return head(rows()); }
+  Eigen::VectorXd head(int n) const {                  // values_->head(laplaceMatSize_), FractionalStepSim.cpp:105-111
+    pull();
+    Eigen::VectorXd v(n);
+    for (int i = 0; i < n; i++) v(i) = h_[i];
+    return v;
+  }
+  HostVector& operator=(const Eigen::VectorXd& v) { h_.resize(v.rows()); for (int i = 0; i < (int)v.rows(); i++) h_[i] = v(i); device_newer_ = false; host_newer_ = true; return *this; }
 #endif
   // facade internals
   void push() { if (host_newer_) { check(set_(g_, h_.data()), "upload"); host_newer_ = false; } }
@@ -79,12 +89,46 @@ class HostVector {
 
 template <class GridT> class BasicMultigrid;
 
+#ifdef MMG_FACADE_HAVE_EIGEN
+typedef Eigen::VectorXd DenseVector;                   // what Grid::residual() returns in the reference (grid.h:47)
+inline std::vector<double> to_std(const Eigen::VectorXd& v) { std::vector<double> o(v.rows()); for (int i = 0; i < (int)v.rows(); i++) o[i] = v(i); return o; }
+inline Eigen::VectorXd operator+(const HostVector& a, const Eigen::VectorXd& b) { return Eigen::VectorXd(a) + b; }
+inline Eigen::VectorXd operator+(const Eigen::VectorXd& a, const HostVector& b) { return a + Eigen::VectorXd(b); }
+inline Eigen::VectorXd operator-(const HostVector& a, const Eigen::VectorXd& b) { return Eigen::VectorXd(a) - b; }
+inline Eigen::VectorXd operator-(const Eigen::VectorXd& a, const HostVector& b) { return a - Eigen::VectorXd(b); }
+// laplaceMat_ / derivXMat_ / derivYMat_ / uvLaplaceMat_ of the reference are host sparse matrices the drivers multiply by host
+// vectors; here they are handles to the device operators and the product runs on the GPU (mmg_grid_apply_matrix)
+struct DeviceMatrix {
+  mmg_grid* g = nullptr;
+  int which = 0, rows = 0, cols = 0;
+  Eigen::VectorXd times(const Eigen::VectorXd& x, double scale) const {
+    std::vector<double> in = to_std(x), out(rows);
+    in.resize(cols, 0.0);
+    check(mmg_grid_apply_matrix(g, which, in.data(), out.data()), "sparse * dense");
+    Eigen::VectorXd y(rows);
+    for (int i = 0; i < rows; i++) y(i) = scale * out[i];
+    return y;
+  }
+};
+struct ScaledDeviceMatrix { const DeviceMatrix* m; double s; };
+inline Eigen::VectorXd operator*(const DeviceMatrix& m, const Eigen::VectorXd& x) { return m.times(x, 1.0); }
+inline Eigen::VectorXd operator*(const DeviceMatrix& m, const HostVector& x) { return m.times(Eigen::VectorXd(x), 1.0); }
+inline ScaledDeviceMatrix operator*(double s, const DeviceMatrix& m) { return ScaledDeviceMatrix{&m, s}; }
+inline Eigen::VectorXd operator*(const ScaledDeviceMatrix& m, const Eigen::VectorXd& x) { return m.m->times(x, m.s); }
+inline Eigen::VectorXd operator*(const ScaledDeviceMatrix& m, const HostVector& x) { return m.m->times(Eigen::VectorXd(x), m.s); }
+#else
+typedef std::vector<double> DenseVector;
+struct DeviceMatrix { mmg_grid* g = nullptr; int which = 0, rows = 0, cols = 0; };
+#endif
+
 // grid.h:20-79
 class Grid {
  public:
   HostVector values_holder_;
   HostVector* values_ = &values_holder_;   // the reference keeps a pointer (grid.h:23): (*grid->values_)(i) still compiles
   HostVector source_;
+  DeviceMatrix laplaceMat_holder_;
+  DeviceMatrix* laplaceMat_ = &laplaceMat_holder_;   // grid.h:25; passed back to sor() by testGmshSingleGrid (testing_functions.cpp:440)
   std::vector<Point> points_;
   std::vector<Boundary> boundaries_;
   GridProperties properties_;
@@ -115,7 +159,13 @@ class Grid {
     const int A = neumannFlag_ ? n + 1 : n;
     values_holder_.bind(h_, A, mmg_grid_get_values, mmg_grid_set_values);
     source_.bind(h_, A, mmg_grid_get_source, mmg_grid_set_source);
+    laplaceMat_holder_ = DeviceMatrix{h_, MMG_MAT_LAPLACE, A, A};
   }
+#ifdef MMG_FACADE_HAVE_EIGEN
+  // the reference's signature: Grid(points, boundaries, properties, Eigen::VectorXd source) grid.h:41
+  Grid(std::vector<Point> points, std::vector<Boundary> boundaries, GridProperties properties, const Eigen::VectorXd& source, int device = 0)
+      : Grid(std::move(points), std::move(boundaries), properties, to_std(source), device) {}
+#endif
   ~Grid() { if (h_ && owned_) mmg_grid_destroy(h_); }
   Grid(const Grid&) = delete;
   Grid& operator=(const Grid&) = delete;
@@ -128,8 +178,10 @@ class Grid {
     boundaries_.at(boundary).values = boundValue;
   }
   void build_normal_vecs(const char* /*filename*/, std::string geomtype) {
-    if (geomtype != "square") throw std::runtime_error("build_normal_vecs: only the square geometry is built in; use mmg_grid_set_normal_vecs");
-    check(mmg_grid_build_normal_vecs_square(h_), "Grid::build_normal_vecs");
+    const int geom = geomtype == "square" ? MMG_GEOM_SQUARE : geomtype == "square_with_circle" ? MMG_GEOM_SQUARE_WITH_CIRCLE
+                     : geomtype == "concentric_circles" ? MMG_GEOM_CONCENTRIC_CIRCLES : -1;
+    if (geom < 0) return;                             // the reference ignores unknown geomtype strings (grid.cpp:442-516)
+    check(mmg_grid_build_normal_vecs(h_, geom), "Grid::build_normal_vecs");
   }
   void rcm_order_points() { sync_flags(); push(); check(mmg_grid_rcm_order_points(h_), "Grid::rcm_order_points"); refresh(); }
   void build_deriv_normal_bound() { sync_flags(); check(mmg_grid_build_deriv_normal_bound(h_), "Grid::build_deriv_normal_bound"); }
@@ -140,11 +192,21 @@ class Grid {
   void bound_eval_neumann() { push(); check(mmg_grid_bound_eval_neumann(h_), "Grid::bound_eval_neumann"); values_->invalidate(); }
   // Grid::sor(laplaceMat_, values_, &source_): the reference always passes its own members (multigrid.cpp:79,93-94,108)
   void sor() { push(); check(mmg_grid_sor(h_, MMG_SMOOTHER_LEXICOGRAPHIC), "Grid::sor"); values_->invalidate(); }
-  std::vector<double> residual() {
+  void sor(DeviceMatrix* matrix, HostVector* values, HostVector* rhs) {          // grid.h:44
+    if (matrix != laplaceMat_ || values != values_ || rhs != &source_) throw std::runtime_error("Grid::sor: the device smoother works on the grid's own members");
+    sor();
+  }
+  DenseVector residual() {
     push();
     std::vector<double> r(values_->rows());
     check(mmg_grid_residual(h_, r.data()), "Grid::residual");
+#ifdef MMG_FACADE_HAVE_EIGEN
+    Eigen::VectorXd out((int)r.size());
+    for (int i = 0; i < (int)r.size(); i++) out(i) = r[i];
+    return out;
+#else
     return r;
+#endif
   }
   void fix_vector_bound_coarse(std::vector<double>* vec) { check(mmg_grid_fix_vector_bound_coarse(h_, vec->data()), "Grid::fix_vector_bound_coarse"); }
   int getSize() const { return laplaceMatSize_; }
@@ -185,6 +247,8 @@ class FractionalStepGrid : public Grid {
   std::string flowType = "kovasznay";
   HostVector u_h_, v_h_, u_old_h_, v_old_h_, u_hat_h_, v_hat_h_;
   HostVector *u = &u_h_, *v = &v_h_, *u_old = &u_old_h_, *v_old = &v_old_h_, *u_hat = &u_hat_h_, *v_hat = &v_hat_h_;
+  DeviceMatrix dx_h_, dy_h_, lap_h_;
+  DeviceMatrix *derivXMat_ = &dx_h_, *derivYMat_ = &dy_h_, *uvLaplaceMat_ = &lap_h_;   // fractionalStepGrid.hpp:16-18
 
   FractionalStepGrid(std::vector<Point> points, std::vector<Boundary> boundaries, GridProperties properties, const std::vector<double>& source, int device = 0)
       : Grid(std::move(points), std::move(boundaries), properties, source, device) {
@@ -193,6 +257,26 @@ class FractionalStepGrid : public Grid {
     u_h_.bind(handle(), n, get<MMG_FS_U>, set<MMG_FS_U>);             v_h_.bind(handle(), n, get<MMG_FS_V>, set<MMG_FS_V>);
     u_old_h_.bind(handle(), n, get<MMG_FS_U_OLD>, set<MMG_FS_U_OLD>); v_old_h_.bind(handle(), n, get<MMG_FS_V_OLD>, set<MMG_FS_V_OLD>);
     u_hat_h_.bind(handle(), n, get<MMG_FS_U_HAT>, set<MMG_FS_U_HAT>); v_hat_h_.bind(handle(), n, get<MMG_FS_V_HAT>, set<MMG_FS_V_HAT>);
+    dx_h_ = DeviceMatrix{handle(), MMG_MAT_DERIVX, n, n}; dy_h_ = DeviceMatrix{handle(), MMG_MAT_DERIVY, n, n}; lap_h_ = DeviceMatrix{handle(), MMG_MAT_UVLAPLACE, n, n};
+  }
+#ifdef MMG_FACADE_HAVE_EIGEN
+  FractionalStepGrid(std::vector<Point> points, std::vector<Boundary> boundaries, GridProperties properties, const Eigen::VectorXd& source, int device = 0)
+      : FractionalStepGrid(std::move(points), std::move(boundaries), properties, to_std(source), device) {}
+#endif
+  void prescribe_soln() {                          // fractionalStepGrid.cpp:26-40: the exact Kovasznay fields (debug helper of check_derivs)
+    const double PI = 3.141592653589793238462643383279502884;
+    const double re = rho / mu;
+    lambda = 0.5 * re - std::sqrt(0.25 * re * re + 4 * PI * PI);
+    for (int i = 0; i < laplaceMatSize_; i++) {
+      const double x = std::get<0>(points_[i]), y = std::get<1>(points_[i]);
+      u->coeffRef(i) = 1 - std::exp(lambda * x) * std::cos(2 * PI * y);
+      v->coeffRef(i) = lambda / (2 * PI) * std::exp(lambda * x) * std::sin(2 * PI * y);
+      u_old->coeffRef(i) = 1 - std::exp(lambda * x) * std::cos(2 * PI * y);
+      v_old->coeffRef(i) = lambda / (2 * PI) * std::exp(lambda * x) * std::sin(2 * PI * y);
+      values_->coeffRef(i) = 0.5 * std::exp(2 * lambda * x);
+    }
+    values_->coeffRef(laplaceMatSize_) = 0;
+    sync_fs();
   }
   void set_uv_bound() {
     if (flowType != "kovasznay") return;          // the reference does nothing for any other flow type (fractionalStepGrid.cpp:45)
@@ -287,6 +371,13 @@ class FractionalStepMultigrid : public BasicMultigrid<FractionalStepGrid> {
   void solveLoop() {}   // empty in the reference too (FracStepMultigrid.cpp:113-115)
 };
 
+}  // namespace mmgf
+
+// Text writers live in their own namespace so that argument-dependent lookup does not find them when the reference's unmodified
+// drivers (which define the same function names) are compiled against this header (cpp/dropin/).
+namespace mmgf_io {
+using mmgf::Grid;
+using mmgf::BasicMultigrid;
 // ---- the reference's text writers, same file names and number format (std::ofstream default: 6 significant digits, one
 // value per line), so the author's plotting scripts read the files unchanged
 inline void writeVectorToTxt(const std::vector<double>& vec, const char* filename) {      // fileReadingFunctions.cpp:70-79
@@ -308,4 +399,5 @@ inline void write_mg_resid(BasicMultigrid<GridT>& mg, const std::string& directo
   writeVectorToTxt(mg.residuals_, (directory + "resid_" + extension + ".txt").c_str());
 }
 
-}  // namespace mmgf
+}  // namespace mmgf_io
+

@@ -16,6 +16,7 @@
 #include "mmg_facade.hpp"
 
 using namespace mmgf;
+using namespace mmgf_io;
 static const double PI = 3.141592653589793238462643383279502884;   // EIGEN_PI as a double
 
 static std::vector<Point> pointsFromMshFile(const char* fname) {

@@ -11,6 +11,7 @@
 #include "mmg_facade.hpp"
 
 using namespace mmgf;
+using namespace mmgf_io;
 static const double pi = 3.141592653589793238462643383279;   // testing_functions.hpp:9
 
 static std::vector<Point> pointsFromMshFile(const char* fname) {

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <cmath>
+
 #include "mmg_internal.hpp"
 
 namespace mmg {
@@ -283,6 +285,29 @@ int mmg_grid_build_normal_vecs_square(mmg_grid* g) {
   }
   API_END
 }
+// Grid::build_normal_vecs(filename, geomtype) grid.cpp:442-516: the square loop over boundaries_[0] runs for every geomtype;
+// "square_with_circle" then gives boundaries_[1] (the hole) outward radial normals about (0.5, 0.5), "concentric_circles" gives
+// boundaries_[0] (outer circle) inward and boundaries_[1] (inner circle) outward radial normals.  O(|boundary|) host work.
+int mmg_grid_build_normal_vecs(mmg_grid* g, int geomtype) {
+  API_BEGIN
+  NEED(g);
+  MMG_REQUIRE(geomtype >= MMG_GEOM_SQUARE && geomtype <= MMG_GEOM_CONCENTRIC_CIRCLES, MMG_ERR_ARG, "build_normal_vecs: unknown geomtype");
+  if (int rc = mmg_grid_build_normal_vecs_square(g)) return rc;
+  Grid& gr = G(g);
+  auto radial = [&](const Boundary& bd, bool outward) {
+    for (int p : bd.pts) {
+      double x = gr.hx[p], y = gr.hy[p];
+      x = x - 0.5; y = y - 0.5;
+      const double norm = std::sqrt(x * x + y * y);
+      x /= norm; y /= norm;
+      gr.hnx[p] = outward ? x : -x; gr.hny[p] = outward ? y : -y;
+    }
+  };
+  if (geomtype != MMG_GEOM_SQUARE) MMG_REQUIRE(gr.boundaries.size() >= 2, MMG_ERR_STATE, "build_normal_vecs: the circle geometries have two boundaries");
+  if (geomtype == MMG_GEOM_SQUARE_WITH_CIRCLE) radial(gr.boundaries[1], true);
+  else if (geomtype == MMG_GEOM_CONCENTRIC_CIRCLES) { radial(gr.boundaries[0], false); radial(gr.boundaries[1], true); }
+  API_END
+}
 int mmg_grid_set_normal_vecs(mmg_grid* g, const double* nx, const double* ny) {
   API_BEGIN
   NEED(g); NEED(nx); NEED(ny);
@@ -428,6 +453,34 @@ int mmg_grid_set_values(mmg_grid* g, const double* in) {
   G(g).sync();
   API_END
 }
+// ranged variants: a rank of a partitioned problem moves only its row block (+ halo) of values_ / source_ across PCIe
+int mmg_grid_get_values_range(mmg_grid* g, int offset, int count, double* out) {
+  API_BEGIN
+  NEED(g); NEED(out);
+  MMG_REQUIRE(offset >= 0 && count >= 0 && offset + count <= G(g).A, MMG_ERR_ARG, "get_values_range: range outside values_");
+  use_device(G(g).device);
+  if (count) MMG_CUDA(cudaMemcpyAsync(out, G(g).x.p + offset, sizeof(double) * count, cudaMemcpyDeviceToHost, G(g).stream));
+  G(g).sync();
+  API_END
+}
+int mmg_grid_set_values_range(mmg_grid* g, int offset, int count, const double* in) {
+  API_BEGIN
+  NEED(g); NEED(in);
+  MMG_REQUIRE(offset >= 0 && count >= 0 && offset + count <= G(g).A, MMG_ERR_ARG, "set_values_range: range outside values_");
+  use_device(G(g).device);
+  if (count) MMG_CUDA(cudaMemcpyAsync(G(g).x.p + offset, in, sizeof(double) * count, cudaMemcpyHostToDevice, G(g).stream));
+  G(g).sync();
+  API_END
+}
+int mmg_grid_set_source_range(mmg_grid* g, int offset, int count, const double* in) {
+  API_BEGIN
+  NEED(g); NEED(in);
+  MMG_REQUIRE(offset >= 0 && count >= 0 && offset + count <= G(g).A, MMG_ERR_ARG, "set_source_range: range outside source_");
+  use_device(G(g).device);
+  if (count) MMG_CUDA(cudaMemcpyAsync(G(g).b.p + offset, in, sizeof(double) * count, cudaMemcpyHostToDevice, G(g).stream));
+  G(g).sync();
+  API_END
+}
 int mmg_grid_get_source(mmg_grid* g, double* out) {
   API_BEGIN
   NEED(g); NEED(out);
@@ -520,6 +573,38 @@ int mmg_grid_get_csr(mmg_grid* g, int which, int* ptr, int* idx, double* val) {
   std::memcpy(ptr, A.ptr.data(), sizeof(int) * A.ptr.size());
   std::memcpy(idx, A.idx.data(), sizeof(int) * A.idx.size());
   std::memcpy(val, A.val.data(), sizeof(double) * A.val.size());
+  API_END
+}
+// y = M x on the device for one of the grid's stencil matrices (host vectors in and out): the reference's drivers multiply
+// derivXMat_ / derivYMat_ / uvLaplaceMat_ by host vectors in check_derivs (FractionalStepSim.cpp:80-113); for laplaceMat_ the
+// dense regularisation row is included.  x has n entries for the derivative operators, A for laplaceMat_.
+int mmg_grid_apply_matrix(mmg_grid* g, int which, const double* x, double* y) {
+  API_BEGIN
+  NEED(g); NEED(x); NEED(y);
+  Grid& gr = G(g);
+  use_device(gr.device);
+  const HybMatrix* M = nullptr;
+  if (which == MMG_MAT_LAPLACE) { MMG_REQUIRE(gr.have_laplacian, MMG_ERR_STATE, "laplaceMat_ has not been built"); M = &gr.Lap; }
+  else {
+    MMG_REQUIRE(gr.fs && gr.fs->have_ops, MMG_ERR_STATE, "apply_matrix: the fractional-step operators have not been built");
+    M = which == MMG_MAT_DERIVX ? &gr.fs->Dx : which == MMG_MAT_DERIVY ? &gr.fs->Dy : which == MMG_MAT_UVLAPLACE ? &gr.fs->Lap : nullptr;
+  }
+  MMG_REQUIRE(M != nullptr, MMG_ERR_ARG, "apply_matrix: which must be MMG_MAT_LAPLACE / DERIVX / DERIVY / UVLAPLACE");
+  const int rows = M->rows + (M->reg_row >= 0 ? 1 : 0);
+  DevBuf<double> dx, dy;
+  dx.upload(x, (size_t)M->cols, gr.stream);
+  dy.alloc((size_t)rows);
+  op_spmv(*M, dx.p, dy.p, gr, MMG_T_OTHER);
+  if (M->reg_row >= 0) {   // dense last row: in-order on the host side of the call is not needed -- a debug product, tree sums are fine
+    std::vector<int> rc = M->reg_col.to_host(gr.stream);
+    std::vector<double> rv = M->reg_val.to_host(gr.stream);
+    double s = M->reg_diag * x[M->reg_row];
+    for (size_t k = 0; k < rc.size(); k++) s += rv[k] * x[rc[k]];
+    dy.download(y, (size_t)M->rows, gr.stream);
+    y[M->reg_row] = s;
+  } else {
+    dy.download(y, (size_t)rows, gr.stream);
+  }
   API_END
 }
 int mmg_grid_set_laplacian_csr(mmg_grid* g, int rows, const int* ptr, const int* idx, const double* val, const double* diags, const int* nb_ptr,
@@ -1025,6 +1110,25 @@ int mmg_solver_solve(mmg_solver* s, double tol, int max_cycles, int extra_bound_
 }
 // multi-GPU: after a partitioned vcycle / solve a rank's values_ are current on its row block and halo ranges only; this
 // collective makes every partitioned level's values_ complete on every rank (grouped ncclBroadcast of the row blocks)
+// rows [own_lo, own_hi) of `level` belong to this rank; its kernels read values_ in [need_lo, need_hi) (block + halo)
+int mmg_solver_owned_range(mmg_solver* s, int level, int* own_lo, int* own_hi, int* need_lo, int* need_hi) {
+  API_BEGIN
+  NEED(s); NEED(own_lo); NEED(own_hi); NEED(need_lo); NEED(need_hi);
+  Solver& so = S(s);
+  MMG_REQUIRE(level >= 0 && level < (int)so.grids.size(), MMG_ERR_ARG, "owned_range: no such level");
+  Grid& g = *so.grids[level];
+  *own_lo = 0; *own_hi = g.A; *need_lo = 0; *need_hi = g.A;
+  if (so.world > 1) {
+    if (!so.dist_ready) { use_device(g.device); dist_setup(so); }
+    const LevelDist& D = so.dist[level];
+    if (D.partitioned) {
+      *own_lo = D.bounds[so.rank]; *own_hi = D.bounds[so.rank + 1];
+      *need_lo = *own_lo; *need_hi = *own_hi;
+      for (const ExchangePlan::Msg& m : D.x_plan.recvs) { *need_lo = std::min(*need_lo, m.offset); *need_hi = std::max(*need_hi, m.offset + m.count); }
+    }
+  }
+  API_END
+}
 int mmg_solver_gather_values(mmg_solver* s) {
   API_BEGIN
   NEED(s);

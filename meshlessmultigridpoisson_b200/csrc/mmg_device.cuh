@@ -41,6 +41,11 @@ __device__ __forceinline__ double ld_relaxed(const double* p) {
   asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {   // polls of words a peer GPU stores with st.relaxed.sys
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }

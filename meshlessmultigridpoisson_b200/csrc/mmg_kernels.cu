@@ -1241,7 +1241,7 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __r
             if (raw != -1) {
               cc[h][t] = raw & 0x7fffffff;
               if (raw < 0) newer |= 1u << (h * ITER + t);
-              xx[h][t] = ld_relaxed((raw < 0 ? xnew : xold) + cc[h][t]);
+              xx[h][t] = PEER ? ld_relaxed_sys((raw < 0 ? xnew : xold) + cc[h][t]) : ld_relaxed((raw < 0 ? xnew : xold) + cc[h][t]);
               if (is_sentinel(xx[h][t])) pend |= 1u << (h * ITER + t);
             } else xx[h][t] = 0.0;
           }
@@ -1254,7 +1254,8 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __r
 #pragma unroll
             for (int t = 0; t < ITER; t++)
               if (pend & (1u << (h * ITER + t))) {
-                xx[h][t] = ld_relaxed(((newer >> (h * ITER + t)) & 1u ? xnew : xold) + cc[h][t]);
+                const double* src = ((newer >> (h * ITER + t)) & 1u ? xnew : xold) + cc[h][t];
+                xx[h][t] = PEER ? ld_relaxed_sys(src) : ld_relaxed(src);     // a neighbour GPU stores these with st.relaxed.sys: same scope on both sides
                 if (!is_sentinel(xx[h][t])) pend &= ~(1u << (h * ITER + t));
               }
           if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); aborted = true; break; }
@@ -2389,6 +2390,16 @@ void dist_setup(Solver& s) {
     (void)coarse;
   }
   if (W > 1 && env_int("MMG_DIST_PEER", 1)) peer_setup(s);
+  // the one-time packed copies are built here, not lazily inside the first sweep: every rank then enters its first peer-memory
+  // sweep at the same time (a rank still packing would let its neighbours' watchdogs run)
+  for (int l = 0; l < L; l++) {
+    LevelDist& D = s.dist[l];
+    Grid& g = *s.grids[l];
+    if (!D.partitioned || !D.peer_ready || g.Lap.n_ovf != 0 || !g.Lap.diag_first) continue;
+    g.mc_row0 = D.bounds[s.rank]; g.mc_row1 = D.bounds[s.rank + 1];
+    g.mc_packed = false;
+    ensure_mc_pack(g);
+  }
   s.dist_ready = true;
 }
 
@@ -2432,16 +2443,16 @@ __global__ void k_peer_init_all(const unsigned char* __restrict__ rowflag, doubl
 // which is what this launch does for the other set: nobody can touch that set before my boundary rows of THIS call
 // have reached the neighbours (they need them to finish their call), so the reset cannot overwrite live data.
 __global__ void k_peer_call_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x, double* cur, double* nxt, size_t stride,
-                                 int iters, int total) {
+                                 int iters, int versions, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const double xi = x[i];
   const bool skipped = rowflag[i] != 0;
   cur[i] = xi;
-  for (int v = 1; v <= iters; v++) {
+  for (int v = 1; v <= iters; v++)
     if (skipped) cur[(size_t)v * stride + i] = xi;
-    nxt[(size_t)v * stride + i] = skipped ? xi : __longlong_as_double((long long)kSentinelBits);
-  }
+  // every version of the other set, not only 1..iters: props.iters may grow again (up to peer_iters) before the next dist_setup
+  for (int v = 1; v <= versions; v++) nxt[(size_t)v * stride + i] = skipped ? xi : __longlong_as_double((long long)kSentinelBits);
 }
 // End of a smoothing call: my rows only waited for the halo values THEY read, so the last version of a halo row of a
 // higher colour may still be in flight from the neighbour.  Wait for each (the sentinel is the "not yet" flag) and
@@ -2450,10 +2461,10 @@ __global__ void k_peer_collect(const double* last, double* x, int offset, int co
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const long long t_start = clock64();
-  double v = ld_relaxed(last + offset + i);
+  double v = ld_relaxed_sys(last + offset + i);
   while (is_sentinel(v)) {
     if (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles) { atomicExch(abort_flag, 1); v = 0.0; break; }
-    v = ld_relaxed(last + offset + i);
+    v = ld_relaxed_sys(last + offset + i);
   }
   x[offset + i] = v;
 }
@@ -2477,7 +2488,7 @@ static bool dist_sor_peer(Solver& s, Grid& g, LevelDist& D) {
   double* cur = D.peer_xs.p + (size_t)D.peer_parity * set_elems;
   double* nxt = D.peer_xs.p + (size_t)(D.peer_parity ^ 1) * set_elems;
   TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * iters / s.world, 3);
-  k_peer_call_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, cur, nxt, stride, iters, g.A);
+  k_peer_call_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, cur, nxt, stride, iters, D.peer_iters, g.A);
   MMG_CUDA(cudaGetLastError());
   const bool ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
     constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;

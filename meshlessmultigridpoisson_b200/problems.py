@@ -23,12 +23,77 @@ def grid_props(poly_deg, iters=5, omega=1.4, rbf_exp=3):
     return dict(rbfExp=rbf_exp, polyDeg=poly_deg, stencilSize=stencil_size(poly_deg), iters=iters, omega=omega)
 
 
-def make_grid(kind, x, y, poly_deg, k1=1, k2=1, fine=True, device=0, **props):
+def _on_circle(x, y, r2):
+    return np.abs(r2 - (x - 0.5) * (x - 0.5) - (y - 0.5) * (y - 0.5)) <= 1e-10        # testing_functions.cpp:101,122,127
+
+
+def _concentric_source(x, y, k1):
+    """testing_functions.cpp:109-121: Laplacian of sin(pi k1 r*), r* = (r - 0.25) / 0.25, as the reference writes it"""
+    x = x - 0.5
+    y = y - 0.5
+    r2 = x * x + y * y
+    rstar = (np.sqrt(r2) - 0.25) / (0.5 - 0.25)
+    out = 0.0
+    for c in (x, y):
+        out = out + (-PI * k1 * k1 * PI * np.sin(PI * k1 * rstar) * (4 * c * r2 ** -0.5) ** 2
+                     + PI * k1 * np.cos(PI * k1 * rstar) * 4 * (r2 ** -0.5 + 2 * c * c * -0.5 * r2 ** -1.5))
+    return out
+
+
+def make_grid(kind, x, y, poly_deg, k1=1, k2=1, fine=True, device=0, geomtype="square", **props):
+    """genGmshGridDirichlet (testing_functions.cpp:68-159) / genGmshGridNeumann (:161-284) for the three geomtypes, plus the mixed
+    variant on the square.  Boundary detection and right-hand sides are evaluated on the host exactly as the drivers do."""
     x = np.ascontiguousarray(x, np.float64)
     y = np.ascontiguousarray(y, np.float64)
     p = grid_props(poly_deg, **props)
     on_b = (x == 0) | (x == 1) | (y == 0) | (y == 1)
     coarse = "fine" if fine else "coarse"
+    if geomtype != "square":
+        assert kind in ("dirichlet", "neumann")
+        outer = on_b if geomtype == "square_with_circle" else _on_circle(x, y, 0.25)
+        inner = _on_circle(x, y, 0.0625) & ~outer
+        po, pi_ = np.nonzero(outer)[0].astype(np.int32), np.nonzero(inner)[0].astype(np.int32)
+        nxo, nyo = x[po] - 0.5, y[po] - 0.5
+        no = np.sqrt(nxo * nxo + nyo * nyo); nxo, nyo = nxo / no, nyo / no
+        nxi, nyi = x[pi_] - 0.5, y[pi_] - 0.5
+        ni = np.sqrt(nxi * nxi + nyi * nyi); nxi, nyi = nxi / ni, nyi / ni
+        if kind == "dirichlet":
+            if geomtype == "square_with_circle":
+                source = -(k1 * k1 + k2 * k2) * PI * PI * np.sin(k1 * PI * x) * np.sin(k1 * PI * y)
+                vo, vi = np.zeros(po.size), np.sin(k1 * PI * x[pi_]) * np.sin(k1 * PI * y[pi_])
+            else:
+                source = _concentric_source(x, y, k1)
+                vo, vi = np.zeros(po.size), np.zeros(pi_.size)
+            g = capi.Grid(x, y, [capi.Boundary(po, vo, type=capi.BC_DIRICHLET), capi.Boundary(pi_, vi, type=capi.BC_DIRICHLET)], p, source, device=device)
+            g.set_implicitFlag(False)
+            g.setBCFlag(0, "dirichlet", vo)
+            g.setBCFlag(1, "dirichlet", vi)
+            g.rcm_order_points()
+            g.build_laplacian()
+            return g
+        source = np.zeros(x.size + 1)
+        if geomtype == "square_with_circle":
+            source[:-1] = -(k1 * k1 + k2 * k2) * PI * PI * np.cos(k1 * PI * x) * np.cos(k2 * PI * y)
+            vo = np.zeros(po.size)
+            vi = -nxi * PI * k1 * np.sin(k1 * PI * x[pi_]) * np.cos(k2 * PI * y[pi_]) - nyi * PI * k2 * np.cos(k1 * PI * x[pi_]) * np.sin(k2 * PI * y[pi_])
+        else:
+            source[:-1] = _concentric_source(x, y, k1)
+            def dn(px, py, nx_, ny_, sign):
+                r = np.sqrt((px - 0.5) ** 2 + (py - 0.5) ** 2)
+                rstar = (r - 0.25) / (0.5 - 0.25)
+                return sign * (nx_ * k1 * PI * np.cos(k1 * PI * rstar) / r * 4 * (px - 0.5)) + sign * (ny_ * k1 * PI * np.cos(k1 * PI * rstar) / r * 4 * (py - 0.5))
+            vo, vi = dn(x[po], y[po], nxo, nyo, -1.0), dn(x[pi_], y[pi_], nxi, nyi, 1.0)
+        g = capi.Grid(x, y, [capi.Boundary(po, vo, type=capi.BC_NEUMANN), capi.Boundary(pi_, vi, type=capi.BC_NEUMANN)], p, source, device=device)
+        g.set_implicitFlag(True)
+        g.setBCFlag(0, "neumann", vo)
+        g.setBCFlag(1, "neumann", vi)
+        g.build_normal_vecs(geomtype)
+        g.rcm_order_points()
+        g.build_deriv_normal_bound()
+        g.build_laplacian()
+        g.modify_coeff_neumann(coarse)
+        g.push_inhomog_to_rhs()
+        return g
     if kind == "dirichlet":
         source = -(k1 * k1 + k2 * k2) * PI * PI * np.sin(k1 * PI * x) * np.sin(k2 * PI * y)
         pts = np.nonzero(on_b)[0].astype(np.int32)
@@ -71,14 +136,14 @@ def make_grid(kind, x, y, poly_deg, k1=1, k2=1, fine=True, device=0, **props):
     return g
 
 
-def make_hierarchy(sizes, kind="dirichlet", fine_poly=4, coarse_poly=3, seed0=1000, jitter=0.3, device=0, cloud="jittered", **kw):
+def make_hierarchy(sizes, kind="dirichlet", fine_poly=4, coarse_poly=3, seed0=1000, jitter=0.3, device=0, cloud="jittered", geomtype="square", **kw):
     """run_mg_sim's set-up (testing_functions.cpp:328-339) on synthetic clouds: one independent jittered lattice
     per level, coarse levels polyDeg 3, finest ``fine_poly``; then buildMatrices()."""
     mg = capi.Multigrid()
     for l, s in enumerate(sizes):
-        x, y = make_cloud(cloud, s, seed0 + l, jitter)
+        x, y = make_cloud(cloud if geomtype == "square" else geomtype, s, seed0 + l, jitter)
         last = l == len(sizes) - 1
-        mg.addGrid(make_grid(kind, x, y, fine_poly if last else coarse_poly, fine=last, device=device, **kw))
+        mg.addGrid(make_grid(kind, x, y, fine_poly if last else coarse_poly, fine=last, device=device, geomtype=geomtype, **kw))
     mg.buildMatrices()
     return mg
 

@@ -15,6 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 KIND_DIRICHLET, KIND_NEUMANN, KIND_PPE, KIND_MIXED = 0, 1, 2, 3
+GEOM_SQUARE, GEOM_SQUARE_WITH_CIRCLE, GEOM_CONCENTRIC_CIRCLES = 0, 1, 2
+GEOM_NAMES = ["square", "square_with_circle", "concentric_circles"]
 MAT_A, MAT_NBC, MAT_R, MAT_P, MAT_DX, MAT_DY, MAT_UVLAP = 0, 1, 2, 3, 4, 5, 6
 VEC_VALUES, VEC_SOURCE, VEC_DIAGS, VEC_U, VEC_V, VEC_UHAT, VEC_VHAT = 0, 1, 2, 3, 4, 5, 6
 
@@ -297,10 +299,10 @@ class Multigrid:
             self.h = None
 
     def add_level(self, kind, x, y, poly_deg, iters=5, omega=1.4, rbf_exp=3, k1=1, k2=1, fine=False, cells=True,
-                  dt=2e-4, mu=0.025, rho=1.0):
+                  dt=2e-4, mu=0.025, rho=1.0, geom=0):
         x = np.ascontiguousarray(x, np.float64)
         y = np.ascontiguousarray(y, np.float64)
-        rc = self.L.orc_mg_add_level(self.h, kind, x.size, x, y, poly_deg, iters, omega, rbf_exp, k1, k2, int(fine), int(cells), dt, mu, rho)
+        rc = self.L.orc_mg_add_level(self.h, kind, x.size, x, y, poly_deg, iters, omega, rbf_exp, k1, k2, int(fine), int(cells) | (int(geom) << 4), dt, mu, rho)
         if rc:
             raise OracleError(self.L.orc_last_error().decode())
 
@@ -367,15 +369,15 @@ class Multigrid:
         return out[:n]
 
 
-def make_hierarchy(sizes, kind=KIND_DIRICHLET, fine_poly=4, coarse_poly=3, fracstep=False, cells=True, seed0=1000, jitter=0.3, cloud="jittered", **kw):
+def make_hierarchy(sizes, kind=KIND_DIRICHLET, fine_poly=4, coarse_poly=3, fracstep=False, cells=True, seed0=1000, jitter=0.3, cloud="jittered", geom=0, **kw):
     """The reference's run_mg_sim set-up (testing_functions.cpp:328-339) on synthetic jittered
     lattices: one independent cloud per level, coarse levels polyDeg 3, finest fine_poly."""
     from meshlessmultigridpoisson_b200.clouds import make_cloud
 
     mg = Multigrid(fracstep=fracstep)
     for l, s in enumerate(sizes):
-        x, y = make_cloud(cloud, s, seed0 + l, jitter)
+        x, y = make_cloud(cloud if geom == 0 else GEOM_NAMES[geom], s, seed0 + l, jitter)
         last = l == len(sizes) - 1
-        mg.add_level(kind, x, y, fine_poly if last else coarse_poly, fine=last, cells=cells, **kw)
+        mg.add_level(kind, x, y, fine_poly if last else coarse_poly, fine=last, cells=cells, geom=geom, **kw)
     mg.build()
     return mg

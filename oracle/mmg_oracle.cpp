@@ -511,6 +511,22 @@ void Grid::build_normal_vecs_square() {  // :442-461 (square branch: inward norm
   }
 }
 
+void Grid::build_normal_vecs(int geom) {  // :442-516 -- the square loop runs for every geomtype, then the circle branches
+  build_normal_vecs_square();
+  auto radial = [&](const Boundary& bd, double sign) {
+    for (size_t b = 0; b < bd.bcPoints.size(); b++) {
+      const Pt& c = points_[bd.bcPoints[b]];
+      double x = c.x, y = c.y;
+      x = x - 0.5; y = y - 0.5;
+      const double normPoint = std::sqrt(x * x + y * y);
+      x /= normPoint; y /= normPoint;
+      normalVecs_[bd.bcPoints[b]] = sign > 0 ? Pt{x, y, 0} : Pt{-x, -y, 0};
+    }
+  };
+  if (geom == GEOM_SQUARE_WITH_CIRCLE) radial(boundaries_.at(1), +1);                       // :480-491
+  else if (geom == GEOM_CONCENTRIC_CIRCLES) { radial(boundaries_.at(0), -1); radial(boundaries_.at(1), +1); }   // :492-515
+}
+
 void Grid::build_deriv_normal_bound() {  // :520-548
   deriv_normal_coeffs_.clear();
   std::vector<std::pair<int, double>> todo;  // (point, value) in reference visiting order
@@ -961,51 +977,129 @@ double Multigrid::residual() {  // multigrid.cpp:112-115 (lpNorm<1>; Eigen's pac
 // ---------------------------------------------------------------------------------
 // Problem factories
 // ---------------------------------------------------------------------------------
-Grid* genGridDirichletSquare(const std::vector<Pt>& points, GridProperties props, int k1, int k2, KnnMode mode) {  // testing_functions.cpp:68-159
+namespace {
+// the manufactured right-hand side of the annulus, u = sin(pi k1 r*) with r* = (r - 0.25) / 0.25, written exactly as
+// testing_functions.cpp:109-121 / :208-221 write it
+double concentric_source(double x, double y, int k1) {
   const double pi = kPi;
-  std::vector<int> bPts;
-  std::vector<double> bValues;
+  x -= 0.5; y -= 0.5;
+  double sum = 0;
+  const double r = std::sqrt(x * x + y * y);
+  const double rstar = (r - 0.25) / (0.5 - 0.25);
+  sum += -pi * k1 * k1 * pi * std::sin(pi * k1 * rstar) * std::pow(4 * x * std::pow(x * x + y * y, -0.5), 2)
+         + pi * k1 * std::cos(pi * k1 * rstar) * 4 * (std::pow(x * x + y * y, -0.5) + 2 * x * x * -0.5 * std::pow(x * x + y * y, -1.5));
+  sum += -pi * k1 * k1 * pi * std::sin(pi * k1 * rstar) * std::pow(4 * y * std::pow(x * x + y * y, -0.5), 2)
+         + pi * k1 * std::cos(pi * k1 * rstar) * 4 * (std::pow(x * x + y * y, -0.5) + 2 * y * y * -0.5 * std::pow(x * x + y * y, -1.5));
+  return sum;
+}
+bool on_circle(double x, double y, double r2) { return std::abs(r2 - (x - 0.5) * (x - 0.5) - (y - 0.5) * (y - 0.5)) <= std::pow(10, -10); }
+}  // namespace
+
+Grid* genGridDirichlet(const std::vector<Pt>& points, GridProperties props, int k1, int k2, KnnMode mode, int geom) {  // testing_functions.cpp:68-159
+  const double pi = kPi;
+  std::vector<int> bPts, bPts_inner;
+  std::vector<double> bValues, bValues_inner;
   std::vector<double> source(points.size());
   for (size_t i = 0; i < points.size(); i++) {
     const double x = points[i].x, y = points[i].y;
-    source[i] = -(k1 * k1 + k2 * k2) * pi * pi * std::sin(k1 * pi * x) * std::sin(k2 * pi * y);
-    if (x == 0 || x == 1 || y == 0 || y == 1) { bPts.push_back((int)i); bValues.push_back(0.0); }
+    if (geom == GEOM_SQUARE) {
+      source[i] = -(k1 * k1 + k2 * k2) * pi * pi * std::sin(k1 * pi * x) * std::sin(k2 * pi * y);
+      if (x == 0 || x == 1 || y == 0 || y == 1) { bPts.push_back((int)i); bValues.push_back(0.0); }
+    } else if (geom == GEOM_SQUARE_WITH_CIRCLE) {   // :92-106 (k1 in both factors, as written)
+      source[i] = -(k1 * k1 + k2 * k2) * pi * pi * std::sin(k1 * pi * x) * std::sin(k1 * pi * y);
+      if (x == 0 || x == 1 || y == 0 || y == 1) { bPts.push_back((int)i); bValues.push_back(0); }
+      else if (on_circle(x, y, 0.0625)) { bPts_inner.push_back((int)i); bValues_inner.push_back(std::sin(k1 * pi * x) * std::sin(k1 * pi * y)); }
+    } else {                                        // :107-135
+      source[i] = concentric_source(x, y, k1);
+      if (on_circle(x, y, 0.25)) { bPts.push_back((int)i); bValues.push_back(0.0); }
+      else if (on_circle(x, y, 0.0625)) { bPts_inner.push_back((int)i); bValues_inner.push_back(0.0); }
+    }
   }
   Boundary boundary;
   boundary.bcPoints = bPts; boundary.type = 1; boundary.values = bValues;
-  Grid* grid = new Grid(points, {boundary}, props, source);
+  std::vector<Boundary> bcs{boundary};
+  if (geom != GEOM_SQUARE) {
+    Boundary inner;
+    inner.bcPoints = bPts_inner; inner.type = 1; inner.values = bValues_inner;
+    bcs.push_back(inner);
+  }
+  Grid* grid = new Grid(points, bcs, props, source);
   grid->knn_mode = mode;
   grid->implicitFlag_ = false;
   grid->setBCFlag(0, "dirichlet", bValues);
+  if (geom != GEOM_SQUARE) grid->setBCFlag(1, "dirichlet", bValues_inner);
   grid->rcm_order_points();
   grid->build_laplacian();
   return grid;
 }
+Grid* genGridDirichletSquare(const std::vector<Pt>& points, GridProperties props, int k1, int k2, KnnMode mode) {
+  return genGridDirichlet(points, props, k1, k2, mode, GEOM_SQUARE);
+}
 
-Grid* genGridNeumannSquare(const std::vector<Pt>& points, GridProperties props, int k1, int k2, const std::string& coarse, KnnMode mode) {  // testing_functions.cpp:161-284
+Grid* genGridNeumann(const std::vector<Pt>& points, GridProperties props, int k1, int k2, const std::string& coarse, KnnMode mode, int geom) {  // testing_functions.cpp:161-284
   const double pi = kPi;
-  std::vector<int> bPts;
-  std::vector<double> bValues;
+  std::vector<int> bPts, bPts_inner;
+  std::vector<double> bValues, bValues_inner;
   std::vector<double> source(points.size() + 1);
   for (size_t i = 0; i < points.size(); i++) {
     const double x = points[i].x, y = points[i].y;
-    source[i] = -(k1 * k1 + k2 * k2) * pi * pi * std::cos(k1 * pi * x) * std::cos(k2 * pi * y);
-    if (x == 0 || x == 1 || y == 0 || y == 1) { bPts.push_back((int)i); bValues.push_back(0.0); }
+    if (geom == GEOM_SQUARE) {
+      source[i] = -(k1 * k1 + k2 * k2) * pi * pi * std::cos(k1 * pi * x) * std::cos(k2 * pi * y);
+      if (x == 0 || x == 1 || y == 0 || y == 1) { bPts.push_back((int)i); bValues.push_back(0.0); }
+    } else if (geom == GEOM_SQUARE_WITH_CIRCLE) {   // :186-207
+      source[i] = -(k1 * k1 + k2 * k2) * pi * pi * std::cos(k1 * pi * x) * std::cos(k2 * pi * y);
+      if (x == 0 || x == 1 || y == 0 || y == 1) { bPts.push_back((int)i); bValues.push_back(0); }
+      else if (on_circle(x, y, 0.0625)) {
+        double normX = x - 0.5, normY = y - 0.5;
+        const double norm = std::sqrt(normX * normX + normY * normY);
+        normX /= norm; normY /= norm;
+        bPts_inner.push_back((int)i);
+        bValues_inner.push_back(-normX * pi * k1 * std::sin(k1 * pi * x) * std::cos(k2 * pi * y) - normY * pi * k2 * std::cos(k1 * pi * x) * std::sin(k2 * pi * y));
+      }
+    } else {                                        // :208-251
+      source[i] = concentric_source(x, y, k1);
+      const double xs = x - 0.5, ys = y - 0.5;
+      const double r = std::sqrt(xs * xs + ys * ys);
+      const double rstar = (r - 0.25) / (0.5 - 0.25);
+      if (on_circle(x, y, 0.25)) {
+        double normX = x - 0.5, normY = y - 0.5;
+        const double norm = std::sqrt(normX * normX + normY * normY);
+        normX /= norm; normY /= norm;
+        bPts.push_back((int)i);
+        bValues.push_back(-normX * k1 * pi * std::cos(k1 * pi * rstar) / r * 4 * (x - 0.5) - normY * k1 * pi * std::cos(k1 * pi * rstar) / r * 4 * (y - 0.5));
+      } else if (on_circle(x, y, 0.0625)) {
+        double normX = x - 0.5, normY = y - 0.5;
+        const double norm = std::sqrt(normX * normX + normY * normY);
+        normX /= norm; normY /= norm;
+        bPts_inner.push_back((int)i);
+        bValues_inner.push_back(normX * k1 * pi * std::cos(k1 * pi * rstar) / r * 4 * (x - 0.5) + normY * k1 * pi * std::cos(k1 * pi * rstar) / r * 4 * (y - 0.5));
+      }
+    }
   }
   source[source.size() - 1] = 0;
   Boundary boundary;
   boundary.bcPoints = bPts; boundary.type = 2; boundary.values = bValues;
-  Grid* grid = new Grid(points, {boundary}, props, source);
+  std::vector<Boundary> bcs{boundary};
+  if (geom != GEOM_SQUARE) {
+    Boundary inner;
+    inner.bcPoints = bPts_inner; inner.type = 2; inner.values = bValues_inner;
+    bcs.push_back(inner);
+  }
+  Grid* grid = new Grid(points, bcs, props, source);
   grid->knn_mode = mode;
   grid->implicitFlag_ = true;
   grid->setBCFlag(0, "neumann", bValues);
-  grid->build_normal_vecs_square();
+  if (geom != GEOM_SQUARE) grid->setBCFlag(1, "neumann", bValues_inner);
+  grid->build_normal_vecs(geom);
   grid->rcm_order_points();
   grid->build_deriv_normal_bound();
   grid->build_laplacian();
   grid->modify_coeff_neumann(coarse);
   grid->push_inhomog_to_rhs();
   return grid;
+}
+Grid* genGridNeumannSquare(const std::vector<Pt>& points, GridProperties props, int k1, int k2, const std::string& coarse, KnnMode mode) {
+  return genGridNeumann(points, props, k1, k2, coarse, mode, GEOM_SQUARE);
 }
 
 FractionalStepGrid* genFractionalStepGrid(const std::vector<Pt>& points, GridProperties props, double dt, double mu, double rho, double ppe_conv,

@@ -58,6 +58,8 @@ struct Boundary { int type = 0; std::vector<int> bcPoints; std::vector<double> v
 struct DerivNormalBC { int pointID; std::vector<double> weights; std::vector<int> neighbors; double value; };
 
 enum KnnMode { KNN_BRUTE = 0, KNN_CELLS = 1 };
+// the geomtype strings of the reference's factories: "square", "square_with_circle", "concentric_circles"
+enum Geom { GEOM_SQUARE = 0, GEOM_SQUARE_WITH_CIRCLE = 1, GEOM_CONCENTRIC_CIRCLES = 2 };
 
 // grid.h:20-79
 struct Grid {
@@ -102,6 +104,7 @@ struct Grid {
   std::pair<std::vector<double>, std::vector<int>> laplaceWeights(int pointID);       // grid.cpp:381-424
   std::pair<std::vector<double>, std::vector<int>> pointInterpWeights(const Pt& p, int polyDeg); // grid.cpp:687-712
   void build_normal_vecs_square();                                                    // grid.cpp:442-461
+  void build_normal_vecs(int geom);                                                   // grid.cpp:442-516 (circle geometries: analytic radial normals)
   void build_deriv_normal_bound();                                                    // grid.cpp:520-548
   void build_laplacian();                                                             // grid.cpp:549-663
   void push_inhomog_to_rhs();                                                         // grid.cpp:664-685
@@ -172,6 +175,9 @@ struct Multigrid {
 // ---- problem factories (the callers the oracle must mirror) -----------------------
 // testing_functions.cpp:68-159 (square branch)
 Grid* genGridDirichletSquare(const std::vector<Pt>& points, GridProperties props, int k1, int k2, KnnMode mode);
+// testing_functions.cpp:68-159 / :161-284 with the hole and annulus branches (two boundaries, analytic normals)
+Grid* genGridDirichlet(const std::vector<Pt>& points, GridProperties props, int k1, int k2, KnnMode mode, int geom);
+Grid* genGridNeumann(const std::vector<Pt>& points, GridProperties props, int k1, int k2, const std::string& coarse, KnnMode mode, int geom);
 // testing_functions.cpp:161-284 (square branch)
 Grid* genGridNeumannSquare(const std::vector<Pt>& points, GridProperties props, int k1, int k2, const std::string& coarse, KnnMode mode);
 // FractionalStepSim.cpp:3-49

@@ -73,10 +73,11 @@ int orc_mg_add_level(void* h, int kind, int n, const double* x, const double* y,
   p.rbfExp = rbfExp; p.polyDeg = polyDeg; p.omega = omega; p.iters = iters;
   p.stencilSize = (int)(2.5 * (polyDeg + 1) * (polyDeg + 2) / 2);  // testing_functions.cpp:378
   const std::string coarse = fine ? "fine" : "coarse";
-  const KnnMode mode = knn_mode ? KNN_CELLS : KNN_BRUTE;
+  const KnnMode mode = (knn_mode & 1) ? KNN_CELLS : KNN_BRUTE;
   Grid* g = nullptr;
-  if (kind == 0) g = genGridDirichletSquare(pts, p, k1, k2, mode);
-  else if (kind == 1) g = genGridNeumannSquare(pts, p, k1, k2, coarse, mode);
+  const int geom = knn_mode >> 4;                    // bits 4..: geometry (0 square, 1 square_with_circle, 2 concentric_circles)
+  if (kind == 0) g = genGridDirichlet(pts, p, k1, k2, mode, geom);
+  else if (kind == 1) g = genGridNeumann(pts, p, k1, k2, coarse, mode, geom);
   else if (kind == 2) g = genFractionalStepGrid(pts, p, dt, mu, rho, 1e-10, coarse, mode);
   else if (kind == 3) g = genGridMixedSquare(pts, p, k1, k2, coarse, mode);
   else throw std::runtime_error("unknown level kind");

@@ -27,7 +27,11 @@ struct Quiet {  // Multigrid::vCycle prints every cycle (multigrid.cpp:69)
 
 extern "C" {
 // kind 0 Dirichlet / 1 Neumann (Multigrid), 2 PPE (FractionalStepMultigrid); files are Gmsh $Nodes files
+void* ref_new_geom(int kind, const char* geomtype, int nfiles, const char** files, const int* polyDeg, int k1, int k2, double dt, double mu, double rho);
 void* ref_new(int kind, int nfiles, const char** files, const int* polyDeg, int k1, int k2, double dt, double mu, double rho) {
+  return ref_new_geom(kind, "square", nfiles, files, polyDeg, k1, k2, dt, mu, rho);
+}
+void* ref_new_geom(int kind, const char* geomtype, int nfiles, const char** files, const int* polyDeg, int k1, int k2, double dt, double mu, double rho) {
   Quiet q;
   Ref* r = new Ref();
   if (kind == 2) r->fmg = new FractionalStepMultigrid(); else r->mg = new Multigrid();
@@ -36,8 +40,8 @@ void* ref_new(int kind, int nfiles, const char** files, const int* polyDeg, int 
     p.iters = 5; p.polyDeg = polyDeg[i]; p.omega = 1.4; p.rbfExp = 3;
     p.stencilSize = (int)(2.5 * (p.polyDeg + 1) * (p.polyDeg + 2) / 2);
     const std::string coarse = (i == nfiles - 1) ? "fine" : "coarse";
-    if (kind == 0) r->mg->addGrid(genGmshGridDirichlet("square", files[i], p, "msh", k1, k2));
-    else if (kind == 1) r->mg->addGrid(genGmshGridNeumann("square", files[i], p, "msh", k1, k2, coarse));
+    if (kind == 0) r->mg->addGrid(genGmshGridDirichlet(geomtype, files[i], p, "msh", k1, k2));
+    else if (kind == 1) r->mg->addGrid(genGmshGridNeumann(geomtype, files[i], p, "msh", k1, k2, coarse));
     else r->fmg->addGrid(genFractionalStepGrid(files[i], p, dt, mu, rho, 1e-10, coarse));
   }
   if (r->mg) r->mg->buildMatrices(); else r->fmg->buildMatrices();
@@ -111,6 +115,10 @@ double ref_fs_step_post(void* h) {
   FractionalStepGrid* g = ((Ref*)h)->fmg->grids_.back().second;
   g->correct_u(); g->correct_v(); g->set_uv_bound();
   return g->fs_residual();
+}
+void ref_fine_bound_eval(void* h) {   // finestGrid->bound_eval_neumann() of the PPE loop (FractionalStepSim.cpp:141)
+  Ref* r = (Ref*)h;
+  r->grid(r->nlev() - 1)->bound_eval_neumann();
 }
 void ref_fs_vec(void* h, int which, double* out) {  // 0 u, 1 v, 2 u_hat, 3 v_hat
   FractionalStepGrid* g = ((Ref*)h)->fmg->grids_.back().second;

@@ -42,12 +42,16 @@ own = slice(int(b[rank]), int(b[rank + 1]))
 ok_hist = np.allclose(hist, ref_hist, rtol=1e-12, atol=0)   # the norm is reduced in a different order (per-rank partials + allreduce)
 ok_x = np.array_equal(x[own], ref_x[own])
 halo_ok = np.array_equal(x, ref_x)
+mg.gather_values()                                          # collective: complete values_ on every rank
+full_ok = np.array_equal(mg.grid(-1).values_, ref_x)
+lo, hi, nlo, nhi = mg.owned_range(-1)
+range_ok = (lo, hi) == (int(b[rank]), int(b[rank + 1])) and nlo <= lo and nhi >= hi
 st = mg.comm_stats()
-flags = torch.tensor([int(ok_hist), int(ok_x)], device="cuda")
+flags = torch.tensor([int(ok_hist), int(ok_x and full_ok and range_ok)], device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("world %d sides %s: history equal to 1e-12 %s, owned solution identical %s (rank0 full vector identical %s); partitioned levels %d, %d messages, %.1f MB sent by rank 0; final residual %.3e"
-          % (world, sides, bool(flags[0].item()), bool(flags[1].item()), halo_ok, st["partitioned_levels"], st["messages"], st["bytes_sent"] / 1e6, hist[-1]))
+    print("world %d sides %s: history equal to 1e-12 %s, owned solution identical %s (rank0 full vector before / after gather_values identical %s / %s); partitioned levels %d, %d messages, %.1f MB sent by rank 0; final residual %.3e"
+          % (world, sides, bool(flags[0].item()), bool(flags[1].item()), halo_ok, full_ok, st["partitioned_levels"], st["messages"], st["bytes_sent"] / 1e6, hist[-1]))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if flags.min().item() == 1 else 1)

@@ -29,6 +29,8 @@ def _ref_lib():
     dp, ip = np.ctypeslib.ndpointer(np.float64), np.ctypeslib.ndpointer(np.int32)
     R.ref_new.restype = C.c_void_p
     R.ref_new.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+    R.ref_new_geom.restype = C.c_void_p
+    R.ref_new_geom.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     R.ref_lv_nnz.restype = C.c_long
     R.ref_lv_nnz.argtypes = [C.c_void_p, C.c_int]
     R.ref_lv_csr.argtypes = [C.c_void_p, C.c_int, ip, ip, dp]
@@ -46,8 +48,9 @@ def _ref_lib():
     return R
 
 
-@pytest.mark.parametrize("kind,fine_poly", [(oracle.KIND_DIRICHLET, 4), (oracle.KIND_DIRICHLET, 6), (oracle.KIND_NEUMANN, 4), (oracle.KIND_PPE, 3)])
-def test_oracle_is_bit_identical_to_the_reference_sources(kind, fine_poly):
+@pytest.mark.parametrize("kind,fine_poly,geom", [(oracle.KIND_DIRICHLET, 4, 0), (oracle.KIND_DIRICHLET, 6, 0), (oracle.KIND_NEUMANN, 4, 0), (oracle.KIND_PPE, 3, 0),
+                                                 (oracle.KIND_DIRICHLET, 4, 1), (oracle.KIND_NEUMANN, 3, 1), (oracle.KIND_DIRICHLET, 4, 2), (oracle.KIND_NEUMANN, 3, 2)])
+def test_oracle_is_bit_identical_to_the_reference_sources(kind, fine_poly, geom):
     """The reference's grid.cpp / multigrid.cpp / FracStepMultigrid.cpp / fractionalStepGrid.cpp, compiled where they lie
     against the Eigen-subset shim and driven through its own Gmsh reader and factories, must agree with the oracle
     restatement bit for bit: operators, right-hand sides, residual history, solution."""
@@ -55,14 +58,16 @@ def test_oracle_is_bit_identical_to_the_reference_sources(kind, fine_poly):
     sizes = [13, 25, 40]
     tmp = tempfile.mkdtemp()
     files = []
+    from meshlessmultigridpoisson_b200.clouds import make_cloud
     for l, s in enumerate(sizes):
-        x, y = jittered_square(s, seed=1000 + l)
+        x, y = make_cloud("jittered" if geom == 0 else oracle.GEOM_NAMES[geom], s, 1000 + l)   # geom 1, 2: the hole and annulus geomtypes (grid.cpp:480-516)
         fn = os.path.join(tmp, "l%d.msh" % l)
         write_msh_nodes(fn, x, y)
         files.append(fn.encode())
     polys = [3] * (len(sizes) - 1) + [fine_poly]
-    h = C.c_void_p(R.ref_new(kind, len(files), (C.c_char_p * len(files))(*files), (C.c_int * len(files))(*polys), 1, 1, 2e-4, 0.025, 1.0))
-    mg = oracle.make_hierarchy(sizes, kind=kind, fine_poly=fine_poly, cells=False, fracstep=(kind == oracle.KIND_PPE))
+    h = C.c_void_p(R.ref_new_geom(kind, oracle.GEOM_NAMES[geom].encode(), len(files), (C.c_char_p * len(files))(*files), (C.c_int * len(files))(*polys), 1, 1,
+                                  2e-4, 0.025, 1.0))
+    mg = oracle.make_hierarchy(sizes, kind=kind, fine_poly=fine_poly, cells=False, fracstep=(kind == oracle.KIND_PPE), geom=geom)
     for l in range(len(sizes)):
         lv = mg.level(l)
         (r, _), ptr, idx, val = lv.csr()
