@@ -120,7 +120,7 @@ static void set_laplacian_csr(Grid& g, int rows, const int* ptr, const int* idx,
     g.nbc.idx.assign(nb_idx, nb_idx + nb_ptr[rows]);
     g.nbc.val.assign(nb_val, nb_val + nb_ptr[rows]);
   }
-  g.have_laplacian = true;
+  g.have_laplacian = true; g.lex_neu_ok = -1;
   g.have_colours = false;
   g.have_blocks = false;
 }

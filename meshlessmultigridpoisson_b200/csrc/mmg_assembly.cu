@@ -773,7 +773,7 @@ void asm_build_laplacian(Grid& g) {
     g.diags.assign(g.A, 0.0);
     ddiag.download(g.diags.data(), N, g.stream);
     g.nbc = HostCsr();
-    g.have_laplacian = true; g.have_colours = false; g.have_blocks = false;
+    g.have_laplacian = true; g.have_colours = false; g.have_blocks = false; g.lex_neu_ok = -1;
     return;
   }
   // Neumann / mixed grid: weights from the device, triplet bookkeeping of grid.cpp:553-661 on the host
@@ -834,7 +834,7 @@ void asm_build_laplacian(Grid& g) {
     csr_from_triplets(A, g.A, g.A, trip);
   }
   hyb_from_csr(g.Lap, A, true, true, g.stream);
-  g.have_laplacian = true; g.have_colours = false; g.have_blocks = false;
+  g.have_laplacian = true; g.have_colours = false; g.have_blocks = false; g.lex_neu_ok = -1;
 }
 
 }  // namespace mmg

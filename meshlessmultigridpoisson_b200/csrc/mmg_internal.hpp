@@ -159,6 +159,7 @@ struct Grid {
   std::vector<double> diags;   // Grid::diags
   HostCsr nbc;                 // neumann_boundary_coeffs_ (only rows near Neumann boundaries are non-empty)
   bool have_laplacian = false;
+  int lex_neu_ok = -1;         // cached: may a Neumann-type grid use the pipelined lexicographic kernel (-1 = not decided yet)
 
   // device state
   DevBuf<double> xs;                     // versioned vectors of the sweep-pipelined lexicographic kernel

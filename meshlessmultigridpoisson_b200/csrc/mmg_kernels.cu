@@ -564,19 +564,125 @@ __device__ long long g_lex_trace[16 * 64];
 __device__ int g_lex_trace_on = 0;
 #define LEX_STAMP(slot) do { if (tracing && lane == 0) g_lex_trace[(warp * 8 + (slot)) % (16 * 64)] = clock64(); } while (0)
 
+// Neumann-type grids in the pipelined kernel (Grid::sor grid.cpp:104-146 with its bound_eval_neumann after every sweep): the
+// dense regularisation row is the LAST row of a sweep and a column of every interior row, so sweep s+1 cannot start before sweep
+// s has finished -- the version vectors express exactly that (every row of sweep s+1 polls xs[s][N]).  One auxiliary CTA per
+// sweep (a) forms the regularisation row's dot product in the reference's order WHILE the sweep runs: its warps turn the
+// entries into products as the rows they read complete, one lane adds them in ascending column order (the serial chain trails
+// the sweep instead of following it); (b) evaluates the Neumann boundary rows of that sweep as their stencils complete.
+struct LexNeumann {
+  int enabled;
+  const int* neu_pts; int n_neu;                  // Neumann boundary nodes, boundary-list order
+  const int* reg_col; const double* reg_val; int reg_len, reg_row; double reg_diag;
+};
+constexpr int kRegRing = 32;                        // blocks of 32 products in flight between the product warps and the adding lane
+
+template <int T, int K>
+__device__ void lex_aux_cta(const HybView& A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b, const double* x_old, double* x_new,
+                            double omega, int* abort_flag, long long timeout_cycles, const LexNeumann& nm, double (*ring)[32], volatile int* ready,
+                            volatile int* consumed) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t_start = clock64();
+  auto poll = [&](const double* p) {
+    double v = ld_relaxed(p);
+    unsigned spins = 0;
+    while (is_sentinel(v)) {
+      if ((++spins & 0xff) == 0 && (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles)) { atomicExch(abort_flag, 1); return 0.0; }
+      v = ld_relaxed(p);
+    }
+    return v;
+  };
+  constexpr int kProd = K / 2;                       // warps 1 .. kProd-1 form products, warps kProd .. K-1 evaluate boundary rows
+  if (threadIdx.x == 0) *consumed = 0;
+  if (threadIdx.x < kRegRing) ready[threadIdx.x] = 0;
+  __syncthreads();
+  const int nblk = (nm.reg_len + 31) / 32;
+  if (warp == 0) {                                   // the adding lane: sum_j val_j x_j, ascending j, one running sum
+    double s = 0.0;
+    for (int blk = 0; blk < nblk; blk++) {
+      unsigned spins = 0;
+      while (ready[blk % kRegRing] != blk + 1) {
+        if ((++spins & 0x3ff) == 0 && (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles)) { atomicExch(abort_flag, 1); break; }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const double2* q = reinterpret_cast<const double2*>(ring[blk % kRegRing]);
+        const int cnt = min(32, nm.reg_len - blk * 32);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          if (2 * i < cnt) { const double2 v = q[i]; s = __dadd_rn(s, v.x); if (2 * i + 1 < cnt) s = __dadd_rn(s, v.y); }
+        }
+        __threadfence_block();
+        *consumed = blk + 1;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {                                 // SOR update of the regularisation row (k_finish_sor_reg / grid.cpp:137-141)
+      const double dot = __dadd_rn(0.0, s);
+      double xi = -dot;
+      xi = __dadd_rn(xi, b[nm.reg_row]);
+      xi = __dmul_rn(xi, omega / nm.reg_diag);
+      xi = __dadd_rn(xi, __dmul_rn(1 - omega, poll(x_old + nm.reg_row)));
+      st_relaxed(x_new + nm.reg_row, xi);
+    }
+  } else if (warp < kProd) {
+    for (int blk = warp - 1; blk < nblk; blk += kProd - 1) {
+      const int j = blk * 32 + lane;
+      double p = 0.0;
+      if (j < nm.reg_len) p = __dmul_rn(nm.reg_val[j], poll(x_new + nm.reg_col[j]));
+      unsigned spins = 0;
+      while (*consumed < blk - kRegRing + 1) {       // the slot still holds an unread block
+        if ((++spins & 0x3ff) == 0 && (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles)) { atomicExch(abort_flag, 1); break; }
+      }
+      ring[blk % kRegRing][lane] = p;
+      __syncwarp();
+      __threadfence_block();
+      if (lane == 0) ready[blk % kRegRing] = blk + 1;
+    }
+  } else {                                           // Grid::bound_eval_neumann for this sweep (k_bound_eval_exact arithmetic, grid.cpp:84-98)
+    for (int i = warp - kProd; i < nm.n_neu; i += K - kProd) {
+      const int row = nm.neu_pts[i];
+      const double* __restrict__ v = row_val(A, row);
+      const int* __restrict__ c = row_col(A, row);
+      const int m = min(A.len[row], A.W);
+      double s = b[row];
+      for (int base = 1; base < m; base += 32) {     // slot 0 is the diagonal; the rest in ascending column order
+        const int k = base + lane;
+        double p = 0.0;
+        if (k < m) p = __dmul_rn(v[k], poll(x_new + c[k]));
+        s = fold_sub32(s, p, min(32, m - base));
+      }
+      if (lane == 0) st_relaxed(x_new + row, s / v[0]);
+    }
+  }
+}
+
 template <int T, int K>
 __global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsigned char* __restrict__ rowflag, const double* __restrict__ b, double* xs,
-                                                          size_t stride, int iters, double omega, int* abort_flag, long long timeout_cycles) {
+                                                          size_t stride, int iters, double omega, int* abort_flag, long long timeout_cycles, int Qarg,
+                                                          LexNeumann nm) {
   __shared__ double xs_s[K];                 // this chunk's new values
   __shared__ unsigned long long bars[K];     // bars[w]: one arrival per in-chunk dependency of row lo+w
   __shared__ unsigned depmask[K];            // bit j of depmask[w]: row lo+w reads row lo+j (j < w)
   __shared__ __align__(16) double prod_s[K][T * 32 + 2];   // per warp: its row's products in column order, for the in-order fold
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sweep = 1 + blockIdx.x % iters;
-  const int q = blockIdx.x / iters, Q = gridDim.x / iters;
-  if (q >= Q) return;
-  const double* x_old = xs + (size_t)(sweep - 1) * stride;
-  double* x_new = xs + (size_t)sweep * stride;
+  const int Q = Qarg;
+  if ((int)blockIdx.x >= Q * iters) {        // auxiliary CTA of a Neumann-type grid: regularisation row + boundary rows of one sweep
+    const int aux = (int)blockIdx.x - Q * iters;
+    if (!nm.enabled || aux >= iters) return;
+    __shared__ __align__(16) double reg_ring[kRegRing][32];
+    __shared__ int reg_ready[kRegRing];
+    __shared__ int reg_consumed;
+    lex_aux_cta<T, K>(A, rowflag, b, xs + (size_t)aux * stride, xs + (size_t)(aux + 1) * stride, omega, abort_flag, timeout_cycles, nm, reg_ring, reg_ready,
+                      &reg_consumed);
+    return;
+  }
+  // Dirichlet-type grids: CTAs are dealt to sweeps (sweep s+1 trails sweep s by one matrix bandwidth).  Neumann-type grids: the
+  // sweeps cannot overlap (see LexNeumann), so every CTA works on every sweep in turn.
+  const int sweep_first = nm.enabled ? 1 : 1 + (int)blockIdx.x % iters;
+  const int sweep_last = nm.enabled ? iters : sweep_first;
+  const int q = nm.enabled ? (int)blockIdx.x : (int)blockIdx.x / iters;
+  const int Qs = nm.enabled ? Q * iters : Q;      // CTAs sharing one sweep
   volatile double* xs_v = xs_s;
   const unsigned bar_me = (unsigned)__cvta_generic_to_shared(&bars[warp]);
   const unsigned bar_lane = (unsigned)__cvta_generic_to_shared(&bars[lane < K ? lane : 0]);
@@ -587,7 +693,10 @@ __global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsig
   if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_me), "r"(K) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   unsigned parity = 0;
-  for (int chunk = q; chunk < nchunks; chunk += Q, parity ^= 1u) {
+  for (int sweep = sweep_first; sweep <= sweep_last; sweep++) {
+  const double* x_old = xs + (size_t)(sweep - 1) * stride;
+  double* x_new = xs + (size_t)sweep * stride;
+  for (int chunk = q; chunk < nchunks; chunk += Qs, parity ^= 1u) {
     const int lo = chunk * K;
     const int row = lo + warp;
     const bool live = row < A.rows && rowflag[row] == 0;
@@ -614,7 +723,9 @@ __global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsig
           pv[t] = v[k];
           const int col = c[k];
           if (col >= lo && col < row && rowflag[col] == 0) { ps[t] = col - lo; in_chunk |= 1u << t; mydeps |= 1u << (col - lo); }
-          else { pp[t] = (col > row ? x_old : x_new) + col; pend_g |= 1u << t; }
+          else {   // a Neumann boundary node keeps, during sweep s, the value bound_eval gave it after sweep s-1
+            pp[t] = ((col > row || (nm.enabled && rowflag[col] == 2)) ? x_old : x_new) + col; pend_g |= 1u << t;
+          }
         }
       }
       wd = omega / v[0];
@@ -715,6 +826,26 @@ __global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsig
         }
       }
       __syncwarp();
+      if (A.n_ovf && A.len[row] > A.W) {          // implicit-Neumann fill-in: the tail holds the row's largest columns, folded last
+        const int o = ovf_find(A, row);
+        const int e = A.ovf_ptr[o + 1];
+        for (int base = A.ovf_ptr[o]; base < e; base += 32) {
+          const int k = base + lane;
+          double p = 0.0;
+          if (k < e) {
+            const int col = A.ovf_col[k];
+            const double* src = ((col > row || rowflag[col] == 2) ? x_old : x_new) + col;
+            double xv = ld_relaxed(src);
+            unsigned sp = 0;
+            while (is_sentinel(xv)) {
+              if ((++sp & 0xff) == 0 && (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles)) { atomicExch(abort_flag, 1); xv = 0.0; break; }
+              xv = ld_relaxed(src);
+            }
+            p = __dmul_rn(A.ovf_val[k], xv);
+          }
+          s = fold_sub32(s, p, e - base);
+        }
+      }
       xi = __dadd_rn(s, bi);
       xi = __dmul_rn(xi, wd);
       xi = __dadd_rn(xi, __dmul_rn(1 - omega, __shfl_sync(0xffffffffu, xo, 0)));
@@ -728,15 +859,18 @@ __global__ void __launch_bounds__(K * 32) k_sor_lex_chunk(HybView A, const unsig
     }
     LEX_STAMP(6);
   }
+  }
 }
 
 // xs[0] = x; xs[s>=1][i] = skipped(i) ? x[i] : sentinel
 __global__ void __launch_bounds__(kBlock) k_pipe_init(const unsigned char* __restrict__ rowflag, const double* __restrict__ x, double* xs, size_t stride,
-                                                      int iters, int total) {
+                                                      int iters, int total, int neumann_rows_are_computed = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const double xi = x[i];
-  const bool skipped = rowflag[i] != 0;
+  // Dirichlet rows are constants of every version; Neumann boundary rows are re-evaluated after every sweep (grid.cpp:144) when the
+  // pipelined lexicographic kernel runs a Neumann-type grid, so their later versions start as "not yet" too
+  const bool skipped = rowflag[i] == 1 || (rowflag[i] == 2 && !neumann_rows_are_computed);
   xs[i] = xi;
   for (int s = 1; s <= iters; s++) xs[(size_t)s * stride + i] = skipped ? xi : __longlong_as_double((long long)kSentinelBits);
 }
@@ -1801,10 +1935,15 @@ static void launch_lex_chunk(Grid& g, size_t stride) {
   int blocks_per_sm = 0;
   MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sor_lex_chunk<T, K>, K * 32, 0));
   const int sms = sm_count_of(g.device);
-  int blocks = std::min(blocks_per_sm * sms, env_int("MMG_LEX_CHUNK_BLOCKS", 1 << 20));
+  const bool neu = g.neumann;
+  int blocks = std::min(blocks_per_sm * sms, env_int("MMG_LEX_CHUNK_BLOCKS", 1 << 20)) - (neu ? iters : 0);   // room for one auxiliary CTA per sweep
   const int need = ((g.Lap.rows + K - 1) / K) * iters;
   if (blocks > need) blocks = need;
   if (blocks < iters) blocks = iters;
+  int Q = blocks / iters;
+  blocks = Q * iters + (neu ? iters : 0);
+  LexNeumann nm{};
+  if (neu) nm = LexNeumann{1, g.neu_pts.p, (int)g.neu_pts.n, g.Lap.reg_col.p, g.Lap.reg_val.p, g.Lap.reg_len, g.Lap.reg_row, g.Lap.reg_diag};
   HybView A = g.Lap.view();
   const unsigned char* rf = g.rowflag.p;
   const double* b = g.b.p;
@@ -1814,7 +1953,7 @@ static void launch_lex_chunk(Grid& g, size_t stride) {
   double omega = g.props.omega;
   int* abortp = g.abort_flag.p;
   long long timeout = 6000000000ll;
-  void* args[] = {&A, &rf, &b, &xs, &st, &it, &omega, &abortp, &timeout};
+  void* args[] = {&A, &rf, &b, &xs, &st, &it, &omega, &abortp, &timeout, &Q, &nm};
   note_kernel(g, "k_sor_lex_chunk", T, K);
   MMG_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_lex_chunk<T, K>, dim3(blocks), dim3(K * 32), args, 0, g.stream));
 }
@@ -1824,9 +1963,10 @@ static void launch_lex_pipe(Grid& g) {
   const int iters = g.props.iters;
   const size_t stride = ((size_t)g.A + 63) / 64 * 64;
   if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
-  k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
+  k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A, g.neumann ? 1 : 0);
   MMG_CUDA(cudaGetLastError());
-  const int chunk = env_int("MMG_LEX_CHUNK", 32);  // rows per CTA chunk of the chunked sweep (0 = warp-per-row pipelined kernel), DESIGN.md §5
+  const int chunk = g.neumann ? 32 : env_int("MMG_LEX_CHUNK", 32);  // rows per CTA chunk of the chunked sweep (0 = warp-per-row pipelined kernel), DESIGN.md §5
+  if constexpr (T > 4) { MMG_REQUIRE(!g.neumann, MMG_ERR_STATE, "pipelined lexicographic sweep on a Neumann-type grid: stencil too wide"); }
   if constexpr (T <= 4) {
     if (chunk > 0) {
       if (chunk == 8) launch_lex_chunk<T, 8>(g, stride);
@@ -1859,7 +1999,22 @@ static void launch_lex_pipe(Grid& g) {
   MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
 }
 
-// all props.iters lexicographic sweeps of a grid without Neumann rows in one pipelined launch
+// A Neumann-type grid runs in the pipelined kernel when its stencil fits the chunked instantiations (W-1 <= 128 entries), the
+// operator is stored diagonal-first and no Neumann boundary row spills into the overflow CSR (they never do: a boundary row has
+// exactly n entries, grid.cpp:520-548).
+static bool lex_neumann_pipelinable(Grid& g) {
+  if (g.lex_neu_ok < 0) {
+    bool ok = g.Lap.reg_row >= 0 && g.Lap.diag_first && g.Lap.W - 1 <= 128 && env_int("MMG_LEX_NEUMANN_PIPE", 1);
+    if (ok && g.Lap.n_ovf) {
+      std::vector<int> ovf = g.Lap.ovf_rows.to_host(g.stream);
+      for (int r : ovf) if (g.bcflags[r] == 2) { ok = false; break; }
+    }
+    g.lex_neu_ok = ok ? 1 : 0;
+  }
+  return g.lex_neu_ok == 1;
+}
+
+// all props.iters lexicographic sweeps of a grid in one pipelined launch
 static bool sor_lex_pipelined(Grid& g) {
   const int Te = (g.Lap.W - 1 + 31) / 32;
   if (Te <= 1) launch_lex_pipe<1>(g);
@@ -2053,7 +2208,10 @@ void op_sor(Grid& g, int smoother) {
   ensure_partials(g, (size_t)kRegBlocks + 2 * (sm_count_of(g.device) * 32 + 8));
   if (smoother == MMG_SMOOTHER_MULTICOLOUR && !g.have_colours) build_colouring(g);
   const int64_t call_bytes = (L.matrix_bytes() + (int64_t)g.A * 28) * g.props.iters;
-  if (smoother == MMG_SMOOTHER_LEXICOGRAPHIC && !g.neumann && g.Lap.n_ovf == 0 && g.props.iters >= 1 && g.Lap.W <= 257 && !env_int("MMG_LEX_NO_PIPE", 0)) {
+  if (smoother == MMG_SMOOTHER_LEXICOGRAPHIC && g.props.iters >= 1 && !env_int("MMG_LEX_NO_PIPE", 0) &&
+      ((!g.neumann && g.Lap.n_ovf == 0 && g.Lap.W <= 257) || (g.neumann && g.exact && lex_neumann_pipelinable(g)))) {
+    // (Neumann-type grids with MMG_ARITH_FAST take the per-sweep path below: its tree-reduced regularisation row makes a sweep
+    // 10 % shorter than the pipelined kernel's in-order chain -- measured 0.66 vs 0.73 s per V-cycle at 1M nodes)
     TimedScope ts(g, MMG_T_SOR, call_bytes, 3);
     sor_lex_pipelined(g);
     return;

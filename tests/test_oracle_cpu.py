@@ -55,7 +55,7 @@ def test_oracle_is_bit_identical_to_the_reference_sources(kind, fine_poly, geom)
     against the Eigen-subset shim and driven through its own Gmsh reader and factories, must agree with the oracle
     restatement bit for bit: operators, right-hand sides, residual history, solution."""
     R = _ref_lib()
-    sizes = [13, 25, 40]
+    sizes = [13, 25, 40] if geom == 0 else [13, 25, 30]      # the reference's kNN is brute force: O(N^2) per pass
     tmp = tempfile.mkdtemp()
     files = []
     from meshlessmultigridpoisson_b200.clouds import make_cloud
