@@ -1253,7 +1253,7 @@ __device__ __forceinline__ void mc_phase_packed(const unsigned char* __restrict_
     for (int h = 0; h < ROWS; h++)
 #pragma unroll
       for (int t = 0; t < ITER; t++) {
-        if (c[h][t] != -1) c[h][t] &= 0x7fffffff;          // bit 31 marks "neighbour of a lower colour" for k_sor_mc_flow
+        if (c[h][t] != -1) c[h][t] &= 0x3fffffff;          // bit 31: neighbour of a lower colour (k_sor_mc_flow); bit 30: overflow tail / previous colour (mmg_stream.cu)
         xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
       }
 #pragma unroll
@@ -1310,14 +1310,17 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_packed(const unsigned char* _
 // tile always has a resident owner whose operands are complete: no deadlock under a cooperative launch; clock64
 // watchdog as in the lexicographic kernels.  Arithmetic per row identical to k_sor_mc_packed.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_mark_lower_colour(unsigned char* chunks, size_t chunk_bytes, int W, int total, const int* __restrict__ colour) {
+__global__ void k_mark_lower_colour(unsigned char* chunks, size_t chunk_bytes, int W, int total, const int* __restrict__ colour, int ncolours) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int* pc = reinterpret_cast<int*>(chunks + (size_t)i * chunk_bytes + (size_t)W * 8);
   const int own = colour[pc[0]];                              // slot 0 is the diagonal
   for (int k = 1; k < W; k++) {
-    const int cn = colour[pc[k]];
-    if (cn >= 0 && cn < own) pc[k] |= 0x80000000;
+    const int col = pc[k];
+    const int cn = colour[col];
+    unsigned m = (unsigned)col;
+    if (cn >= 0 && cn < own) m |= 0x80000000u;                // bit 31: k_sor_mc_flow reads the newer version
+    pc[k] = (int)m;
   }
 }
 
@@ -1373,7 +1376,7 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc_flow(const unsigned char* __r
           for (int t = 0; t < ITER; t++) {
             const int raw = cc[h][t];
             if (raw != -1) {
-              cc[h][t] = raw & 0x7fffffff;
+              cc[h][t] = raw & 0x3fffffff;
               if (raw < 0) newer |= 1u << (h * ITER + t);
               xx[h][t] = PEER ? ld_relaxed_sys((raw < 0 ? xnew : xold) + cc[h][t]) : ld_relaxed((raw < 0 ? xnew : xold) + cc[h][t]);
               if (is_sentinel(xx[h][t])) pend |= 1u << (h * ITER + t);
@@ -1469,7 +1472,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sor_mc_small(const unsigne
       const int k = gl + t * LPR;
       const bool ok = valid && k < W;
       nv[t] = ok ? ldg_stream_f64(pv + k, stream) : 0.0;
-      nc[t] = ok ? (ldg_stream_s32(pc + k, stream) & 0x7fffffff) : -1;
+      nc[t] = ok ? (ldg_stream_s32(pc + k, stream) & 0x3fffffff) : -1;
     }
   };
   const int nphases = iters * ncolours;
@@ -2858,7 +2861,7 @@ void ensure_mc_pack(Grid& g) {
     MMG_CUDA(cudaGetLastError());
     DevBuf<int> dcol;
     dcol.upload(g.colour_host, g.stream);
-    k_mark_lower_colour<<<(total_int + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, total_int, dcol.p);
+    k_mark_lower_colour<<<(total_int + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, total_int, dcol.p, n_int);
     MMG_CUDA(cudaGetLastError());
     if (g.Lap.n_ovf) {
       k_mark_overflow<<<(total + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.mc_chunks.p, g.Lap.chunk_bytes, g.Lap.W, total, g.Lap.len.p);

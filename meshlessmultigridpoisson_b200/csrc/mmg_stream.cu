@@ -69,10 +69,11 @@ struct RingCtl {
   int phase[kMaxStages], row0[kMaxStages], nrows[kMaxStages];
 };
 
-__device__ __forceinline__ RingCtl* ring_setup(unsigned char* smem, int stages, unsigned tile_bytes) {
+__device__ __forceinline__ RingCtl* ring_setup(unsigned char* smem, int stages, unsigned tile_bytes, unsigned full_arrivals = 1) {
   RingCtl* C = reinterpret_cast<RingCtl*>(smem + (size_t)stages * tile_bytes);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; s++) { mbar_init(&C->full[s], 1); mbar_init(&C->empty[s], kConsumerWarps); }
+    for (int s = 0; s < stages; s++) { mbar_init(&C->full[s], full_arrivals); mbar_init(&C->empty[s], kConsumerWarps); }
+
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -487,9 +488,9 @@ bool stream_sor_mc(Grid& g) {
   return dispatch_lanes(L.W, prefer, [&](auto Lc, auto I) {
     constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
     const int rows_used = rows_pref >= 2 ? 2 : 1;
-    auto kern = rows_used == 2 ? k_sor_mc_tma<LPR, ITER, 2> : k_sor_mc_tma<LPR, ITER, 1>;
     const unsigned tile_bytes = (unsigned)(kConsumerWarps * (32 / LPR) * rows_used * L.chunk_bytes);
     const int sms = sm_count(g.device);
+    auto kern = rows_used == 2 ? k_sor_mc_tma<LPR, ITER, 2> : k_sor_mc_tma<LPR, ITER, 1>;
     // measured on the 4M-row level, n=37 (profiles/r02_tma_sweep.txt): 3 CTAs x 2 stages x 64-row tiles 4789 GB/s; 2 CTAs x 3 stages 4463;
     // 32-row tiles 3204 (2 CTAs) ... 4403 (4 CTAs): the consumers are latency bound on the gathers, so resident warps count
     RingShape rs = ring_shape(tile_bytes, env_int("MMG_TMA_CTAS", 3), env_int("MMG_TMA_STAGES", 0), env_int("MMG_TMA_SMEM_KB", 180));

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 SIDES_250K = [32, 63, 125, 250, 500]
 SIDES_1M = [32, 63, 125, 250, 500, 1000]          # BASELINE config 2: 1M nodes, 6 levels
-MC_KNOBS = ("MMG_MC_FLOW", "MMG_MC_FLOW_MAX_ROWS", "MMG_MC_TMA", "MMG_MC_PACKED", "MMG_SPMV_TMA")
+MC_KNOBS = ("MMG_MC_FLOW", "MMG_MC_FLOW_MAX_ROWS", "MMG_MC_TMA", "MMG_MC_PACKED", "MMG_SPMV_TMA", "MMG_TMA_FLOW")
 
 
 @pytest.fixture(scope="module")
@@ -87,8 +87,8 @@ MC_VARIANTS = {
 
 @pytest.mark.parametrize("variant", sorted(MC_VARIANTS))
 def test_fast_multicolour_sweep_at_size(h250k, monkeypatch, variant):
-    """the instantiations bench.py times (finest level: TMA-fed packed sweep; next level: barrier-free sweep) vs Grid-level
-    restatement of the multicolour smoother (rows of one colour updated from the state before the phase)"""
+    """the instantiations bench.py times (finest level: TMA-fed sweep; next level: barrier-free sweep) and the register-fed fallback
+    vs the oracle's Grid-level restatement of the multicolour smoother (rows of one colour updated from the state before the phase)"""
     gpu, ref = h250k
     env, kernel = MC_VARIANTS[variant]
     clean_env(monkeypatch, **env)
