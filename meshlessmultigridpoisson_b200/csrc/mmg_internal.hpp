@@ -283,6 +283,8 @@ void build_colouring(Grid& g);
 void ensure_mc_pack(Grid& g);
 // mmg_stream.cu: TMA-fed (cp.async.bulk + mbarrier ring) multicolour sweep and SpMV-class operators; false = no instantiation
 bool stream_sor_mc(Grid& g);
+struct PeerSends;
+bool stream_sor_mc_flow(Grid& g, double* xs, size_t stride, const PeerSends* peers);
 bool stream_spmv(const HybMatrix& M, const double* x, const double* b, double* y, const unsigned char* rowflag, int op, int mask_d, int mask_n,
                  double* partial, int* nblocks_out, int device, cudaStream_t s, int row0, int nrows);
 void peer_setup(Solver& s);          // mmg_comm.cu: IPC exchange of the versioned-vector allocations of the partitioned levels

@@ -2273,7 +2273,13 @@ void op_sor(Grid& g, int smoother) {
         const int iters = g.props.iters;
         const size_t stride = ((size_t)g.A + 63) / 64 * 64;
         if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
-        ok = launch_packed_family(g, [&](auto Lc, auto I) {
+        if (g.A >= env_int("MMG_MC_TMAFLOW_MIN_ROWS", 100000) && env_int("MMG_MC_TMAFLOW", 1)) {     // the same sweep, operator fed through the TMA ring
+          k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
+          MMG_CUDA(cudaGetLastError());
+          ok = stream_sor_mc_flow(g, g.xs.p, stride, nullptr);
+          if (ok) MMG_CUDA(cudaMemcpyAsync(g.x.p, g.xs.p + (size_t)iters * stride, sizeof(double) * g.A, cudaMemcpyDeviceToDevice, g.stream));
+        }
+        if (!ok) ok = launch_packed_family(g, [&](auto Lc, auto I) {
           constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
           k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
           MMG_CUDA(cudaGetLastError());
@@ -2651,7 +2657,17 @@ static bool dist_sor_peer(Solver& s, Grid& g, LevelDist& D) {
   TimedScope ts(g, MMG_T_SOR, (L.matrix_bytes() + (int64_t)g.A * 28) * iters / s.world, 3);
   k_peer_call_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, cur, nxt, stride, iters, D.peer_iters, g.A);
   MMG_CUDA(cudaGetLastError());
-  const bool ok = dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
+  bool tma_done = false;
+  if (g.mc_colour_ptr.back() >= env_int("MMG_MC_TMAFLOW_MIN_ROWS", 100000) && env_int("MMG_MC_TMAFLOW", 1)) {
+    PeerSends peers{};
+    peers.n = D.n_sends;
+    for (int k = 0; k < D.n_sends; k++) {
+      peers.lo[k] = D.send_lo[k]; peers.hi[k] = D.send_hi[k];
+      peers.base[k] = D.send_base[k] + (size_t)D.peer_parity * set_elems;
+    }
+    tma_done = stream_sor_mc_flow(g, cur, stride, &peers);
+  }
+  const bool ok = tma_done || dispatch_lpr_iter(L.W, [&](auto Lc, auto I) {
     constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
     const int rows_used = env_int("MMG_MC_FLOW_ROWS", 1) == 1 ? 1 : 2;
     void* kern = rows_used == 1 ? (void*)k_sor_mc_flow<LPR, ITER, 1, true> : (void*)k_sor_mc_flow<LPR, ITER, 2, true>;

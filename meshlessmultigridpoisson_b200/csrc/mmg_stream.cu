@@ -305,6 +305,153 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-fed barrier-free sweep: the stream of k_sor_mc_tma with the synchronisation of k_sor_mc_flow (mmg_kernels.cu).
+// Every sweep writes its own version xs[s+1] of the vector, whose swept rows start as the sentinel NaN; a row of colour c
+// reads neighbours of a lower colour from xs[s+1] (bit 31 of the packed column) and everything else from xs[s], polling with
+// ld.relaxed while it sees the sentinel -- the values are the ready flags, there is no barrier and no fence.  Tiles are taken
+// in (sweep, colour, tile) order and every CTA works through its tiles in that order, so the lowest unfinished tile always has a
+// resident owner whose operands are complete (cooperative launch, clock64 watchdog).  For the levels that are too small to
+// amortise a colour barrier (<= 1.5M rows) and, with PEER, for a rank's row block of a partitioned level: a row next to a cut
+// is also stored into the neighbour rank's copy of the same version over NVLink (st.relaxed.sys), where that rank's rows poll it.
+// Per-row arithmetic and lane mapping of k_sor_mc_flow / k_sor_mc_packed: same bits.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int ITER, int ROWS, bool PEER>
+__global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma_flow(const unsigned char* __restrict__ chunks, unsigned chunk_bytes, int W,
+                                                                    const int* __restrict__ phase_ptr, int pps, int iters, const double* __restrict__ b,
+                                                                    double* xs, size_t stride, double omega, int* ctl, int stages, int dynamic,
+                                                                    int* abort_flag, long long timeout_cycles, PeerSends peers) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int GPW = 32 / LPR;
+  constexpr int TR = kConsumerWarps * GPW * ROWS;
+  const unsigned tile_bytes = TR * chunk_bytes;
+  RingCtl* C = ring_setup(smem, stages, tile_bytes);
+  const int nphases = iters * pps;
+  int* tickets = ctl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kConsumerWarps) {                          // ---- producer (as in k_sor_mc_tma)
+    if (lane != 0) return;
+    const unsigned long long pol = policy_evict_first();
+    int s = 0;
+    unsigned par = 0;
+    int phase = 0;
+    int ticket = dynamic ? atomicAdd(&tickets[0], 1) : (int)blockIdx.x;
+    for (;;) {
+      int t = ticket, first = 0, count = 0;
+      while (phase < nphases) {
+        const int c = phase % pps;
+        first = phase_ptr[c];
+        count = phase_ptr[c + 1] - first;
+        if (t < (count + TR - 1) / TR) break;
+        if (++phase < nphases) t = dynamic ? atomicAdd(&tickets[phase], 1) : (int)blockIdx.x;
+      }
+      mbar_wait(&C->empty[s], par ^ 1u);
+      if (phase >= nphases) {
+        C->phase[s] = nphases;
+        mbar_arrive(&C->full[s]);
+        return;
+      }
+      ticket = dynamic ? atomicAdd(&tickets[phase], 1) : t + (int)gridDim.x;
+      const int r0 = first + t * TR;
+      const int n = min(TR, count - t * TR);
+      C->phase[s] = phase; C->row0[s] = r0; C->nrows[s] = n;
+      const unsigned bytes = (unsigned)n * chunk_bytes;
+      mbar_arrive_expect_tx(&C->full[s], bytes);
+      bulk_g2s(smem + (size_t)s * tile_bytes, chunks + (size_t)r0 * chunk_bytes, bytes, &C->full[s], pol);
+      if (++s == stages) { s = 0; par ^= 1u; }
+    }
+  }
+
+  // ---- consumers
+  const int gl = lane % LPR, q = lane / LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const double om1 = 1 - omega;
+  const long long t_start = clock64();
+  int s = 0;
+  unsigned par = 0;
+  for (;;) {
+    mbar_wait(&C->full[s], par);
+    const int ph = C->phase[s];
+    if (ph >= nphases) return;
+    const int it = ph / pps;
+    const double* xold = xs + (size_t)it * stride;
+    double* xnew = xs + (size_t)(it + 1) * stride;
+    const int n = C->nrows[s];
+    const unsigned char* tile = smem + (size_t)s * tile_bytes;
+    double v[ROWS][ITER], xx[ROWS][ITER], bi[ROWS], acc[ROWS];
+    int c[ROWS][ITER];
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      const int lr = h * (kConsumerWarps * GPW) + warp * GPW + q;
+      tile_row_fetch<LPR, ITER>(tile, chunk_bytes, W, lr, lr < n, gl, v[h], c[h]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&C->empty[s]);
+    if (++s == stages) { s = 0; par ^= 1u; }
+    unsigned pend = 0, newer = 0;
+#pragma unroll
+    for (int h = 0; h < ROWS; h++)
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        const int raw = c[h][t];
+        if (raw != -1) {
+          c[h][t] = raw & kColMask;
+          if (raw < 0) newer |= 1u << (h * ITER + t);
+          const double* src = (raw < 0 ? xnew : xold) + c[h][t];
+          xx[h][t] = PEER ? ld_relaxed_sys(src) : ld_relaxed(src);
+          if (is_sentinel(xx[h][t])) pend |= 1u << (h * ITER + t);
+        } else xx[h][t] = 0.0;
+      }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) bi[h] = (gl == 0 && c[h][0] != -1) ? b[c[h][0]] : 0.0;
+    bool aborted = false;
+    unsigned spins = 0;
+    while (__any_sync(0xffffffffu, pend != 0)) {         // rare: an operand of this tile is still being computed
+#pragma unroll
+      for (int h = 0; h < ROWS; h++)
+#pragma unroll
+        for (int t = 0; t < ITER; t++)
+          if (pend & (1u << (h * ITER + t))) {
+            const double* src = ((newer >> (h * ITER + t)) & 1u ? xnew : xold) + c[h][t];
+            xx[h][t] = PEER ? ld_relaxed_sys(src) : ld_relaxed(src);
+            if (!is_sentinel(xx[h][t])) pend &= ~(1u << (h * ITER + t));
+          }
+      if ((++spins & 0x3f) == 0 && (*(volatile int*)abort_flag || clock64() - t_start > timeout_cycles)) { atomicExch(abort_flag, 1); aborted = true; break; }
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      double a = 0.0;
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        if (t == 0 && gl == 0) continue;
+        a = __dsub_rn(a, __dmul_rn(v[h][t], xx[h][t]));
+      }
+      acc[h] = a;
+    }
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) acc[h] = group_sum<LPR>(acc[h], gmask);
+    if (gl == 0) {
+#pragma unroll
+      for (int h = 0; h < ROWS; h++) {
+        if (c[h][0] != -1) {
+          double xi = __dadd_rn(acc[h], bi[h]);
+          xi = __dmul_rn(xi, omega / v[h][0]);
+          xi = __dadd_rn(xi, __dmul_rn(om1, xx[h][0]));
+          const int row = c[h][0];
+          if (aborted) xi = 0.0;                          // on abort: unblock everyone behind us
+          st_relaxed(xnew + row, xi);
+          if (PEER) {
+            if (peers.n > 0 && row >= peers.lo[0] && row < peers.hi[0]) st_relaxed_sys(peers.base[0] + (size_t)(it + 1) * stride + row, xi);
+            if (peers.n > 1 && row >= peers.lo[1] && row < peers.hi[1]) st_relaxed_sys(peers.base[1] + (size_t)(it + 1) * stride + row, xi);
+          }
+        }
+      }
+    }
+    if (aborted) return;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SpMV-class operators over the natural-order row chunks: y = op(A, x) for rows [row0, row0 + nrows) (ops as in k_spmv2).
 // Static round-robin tiles (no inter-CTA dependency: a plain launch), same ring.
 // ------------------------------------------------------------------------------------------------
@@ -522,6 +669,58 @@ bool stream_sor_mc(Grid& g) {
     void* args[] = {&chunks, &cb, &W, &cp, &ppsv, &bnd_phase, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &debug_flags, &A, &reg};
     note_kernel(g, "k_sor_mc_tma", LPR, ITER, rows_used);
     MMG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(blocks), dim3(kStreamThreads), args, rs.smem, g.stream));
+  });
+}
+
+// Barrier-free TMA-fed sweep over the versioned vectors xs (iters+1 versions of `stride` doubles, version 0 = values_, swept rows
+// of the later versions = sentinel): all phases of the call in one cooperative launch.  `peers` non-null: rows next to a cut are
+// mirrored into the neighbour ranks' vectors.  False when the stencil width has no instantiation.
+bool stream_sor_mc_flow(Grid& g, double* xs, size_t stride, const PeerSends* peers) {
+  const HybMatrix& L = g.Lap;
+  int prefer = g.A < 200000 ? 0 : (L.W > 16 && L.W <= 40) ? 8 : (L.W > 40 && L.W <= 80) ? 16 : 0;
+  if (env_int("MMG_TMA_LPR", 0)) prefer = env_int("MMG_TMA_LPR", 0);
+  // measured (profiles/r02_tma_sweep7.txt): 1M rows: 64-row tiles x 3 CTAs 3620 GB/s, 32-row tiles x 4 CTAs 3200 (register-fed
+  // k_sor_mc_flow: 2760); 250k rows: 1630 vs 1890 (1720) -- the smaller level wants more, smaller tiles in flight
+  const int swept = g.mc_colour_ptr.back();
+  const int rows_pref = env_int("MMG_TMAFLOW_ROWS", swept >= 500000 ? 2 : 1);
+  const int ctas_pref = env_int("MMG_TMAFLOW_CTAS", swept >= 500000 ? 3 : 4);
+  return dispatch_lanes(L.W, prefer, [&](auto Lc, auto I) {
+    constexpr int LPR = decltype(Lc)::value, ITER = decltype(I)::value;
+    const int rows_used = rows_pref >= 2 ? 2 : 1;
+    void* kern = peers ? (rows_used == 2 ? (void*)k_sor_mc_tma_flow<LPR, ITER, 2, true> : (void*)k_sor_mc_tma_flow<LPR, ITER, 1, true>)
+                       : (rows_used == 2 ? (void*)k_sor_mc_tma_flow<LPR, ITER, 2, false> : (void*)k_sor_mc_tma_flow<LPR, ITER, 1, false>);
+    const unsigned tile_bytes = (unsigned)(kConsumerWarps * (32 / LPR) * rows_used * L.chunk_bytes);
+    const int sms = sm_count(g.device);
+    RingShape rs = ring_shape(tile_bytes, ctas_pref, env_int("MMG_TMAFLOW_STAGES", 0), env_int("MMG_TMAFLOW_SMEM_KB", 180));
+    MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs.smem));
+    int blocks_per_sm = 0;
+    MMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, (const void*)kern, kStreamThreads, rs.smem));
+    MMG_REQUIRE(blocks_per_sm >= 1, MMG_ERR_CUDA, "k_sor_mc_tma_flow does not fit an SM");
+    const int pps = (int)g.mc_colour_ptr.size() - 1;
+    const int TR = kConsumerWarps * (32 / LPR) * rows_used;
+    int maxtiles = 1;
+    for (int c = 0; c < pps; c++) maxtiles = std::max(maxtiles, (g.mc_colour_ptr[c + 1] - g.mc_colour_ptr[c] + TR - 1) / TR);
+    const int blocks = std::min(std::min(blocks_per_sm, rs.ctas_per_sm) * sms, maxtiles);
+    const int nphases = pps * g.props.iters;
+    if (g.mc_ctl.n < (size_t)2 * nphases) g.mc_ctl.alloc((size_t)2 * nphases);
+    MMG_CUDA(cudaMemsetAsync(g.mc_ctl.p, 0, sizeof(int) * 2 * nphases, g.stream));
+    const unsigned char* chunks = g.mc_chunks.p;
+    unsigned cb = (unsigned)L.chunk_bytes;
+    int W = L.W;
+    const int* cp = g.mc_colour_ptr_dev.p;
+    int iters = g.props.iters, ppsv = pps;
+    const double* b = g.b.p;
+    size_t st = stride;
+    double omega = g.props.omega;
+    int* ctl = g.mc_ctl.p;
+    int stages = rs.stages, dynamic = env_int("MMG_TMA_DYNAMIC", 1);
+    int* abortp = g.abort_flag.p;
+    long long timeout = 6000000000ll;
+    PeerSends ps{};
+    if (peers) ps = *peers;
+    void* args[] = {&chunks, &cb, &W, &cp, &ppsv, &iters, &b, &xs, &st, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &ps};
+    note_kernel(g, peers ? "k_sor_mc_tma_flow_peer" : "k_sor_mc_tma_flow", LPR, ITER, rows_used);
+    MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kStreamThreads), args, rs.smem, g.stream));
   });
 }
 

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 SIDES_250K = [32, 63, 125, 250, 500]
 SIDES_1M = [32, 63, 125, 250, 500, 1000]          # BASELINE config 2: 1M nodes, 6 levels
-MC_KNOBS = ("MMG_MC_FLOW", "MMG_MC_FLOW_MAX_ROWS", "MMG_MC_TMA", "MMG_MC_PACKED", "MMG_SPMV_TMA", "MMG_TMA_FLOW")
+MC_KNOBS = ("MMG_MC_FLOW", "MMG_MC_FLOW_MAX_ROWS", "MMG_MC_TMA", "MMG_MC_PACKED", "MMG_SPMV_TMA", "MMG_MC_TMAFLOW", "MMG_MC_TMAFLOW_MIN_ROWS")
 
 
 @pytest.fixture(scope="module")
@@ -81,7 +81,8 @@ def test_schedules_bit_exact_at_size(h250k):
 MC_VARIANTS = {
     "tma": (dict(MMG_MC_FLOW_MAX_ROWS="0"), "k_sor_mc_tma<8,5"),
     "packed": (dict(MMG_MC_FLOW_MAX_ROWS="0", MMG_MC_TMA="0"), "k_sor_mc_packed<8,5,2>"),
-    "flow": (dict(), "k_sor_mc_flow<8,5,1>"),
+    "tma_flow": (dict(), "k_sor_mc_tma_flow<8,5,"),
+    "flow": (dict(MMG_MC_TMAFLOW="0"), "k_sor_mc_flow<8,5,1>"),
 }
 
 

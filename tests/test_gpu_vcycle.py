@@ -151,14 +151,14 @@ def test_block_lexicographic_with_one_block_is_the_reference_sweep(libmmg):
 def test_fast_multicolour_sweep_variants_are_bit_identical(libmmg, monkeypatch):
     """The throughput-mode multicolour sweep has several schedules of the same per-row arithmetic: per-colour launches over
     the natural-order operator; over the colour-major packed copy the TMA-fed ring with counter barriers (k_sor_mc_tma), the
-    register-fed kernel with grid.sync (k_sor_mc_packed), the barrier-free sweep (k_sor_mc_flow), and on the coarsest levels
+    register-fed kernel with grid.sync (k_sor_mc_packed), the barrier-free sweep register-fed (k_sor_mc_flow) or TMA-fed (k_sor_mc_tma_flow), and on the coarsest levels
     the single-CTA kernels with the vectors (k_sor_mc_small) or the whole operator (k_sor_mc_resident) in shared memory.
     Rows of one colour are independent, so all must produce the same bits -- a stale read across a barrier shows up here."""
     from meshlessmultigridpoisson_b200.problems import make_hierarchy
 
-    knobs = ("MMG_MC_PACKED", "MMG_MC_SMALL", "MMG_MC_FLOW", "MMG_MC_TMA", "MMG_MC_RESIDENT", "MMG_MC_FLOW_MAX_ROWS", "MMG_TMA_ROWS", "MMG_TMA_DYNAMIC", "MMG_TMA_FLOW")
+    knobs = ("MMG_MC_PACKED", "MMG_MC_SMALL", "MMG_MC_FLOW", "MMG_MC_TMA", "MMG_MC_RESIDENT", "MMG_MC_FLOW_MAX_ROWS", "MMG_TMA_ROWS", "MMG_TMA_DYNAMIC", "MMG_MC_TMAFLOW_MIN_ROWS")
     results = []
-    for env in ({"MMG_MC_PACKED": "0"}, {}, {"MMG_MC_FLOW": "0"}, {"MMG_MC_FLOW": "0", "MMG_TMA_ROWS": "1", "MMG_TMA_DYNAMIC": "0"},
+    for env in ({"MMG_MC_PACKED": "0"}, {}, {"MMG_MC_TMAFLOW_MIN_ROWS": "0"}, {"MMG_MC_FLOW": "0"}, {"MMG_MC_FLOW": "0", "MMG_TMA_ROWS": "1", "MMG_TMA_DYNAMIC": "0"},
                 {"MMG_MC_FLOW": "0", "MMG_MC_TMA": "0"}, {"MMG_MC_SMALL": "0"}, {"MMG_MC_RESIDENT": "0"}, {"MMG_MC_RESIDENT": "0", "MMG_MC_SMALL": "0"}):
         for k in knobs:
             monkeypatch.delenv(k, raising=False)
