@@ -346,7 +346,8 @@ def main():
     own_lo, own_hi, need_lo, need_hi = mg.owned_range(-1) if world > 1 else (0, A, 0, A)
     src = torch.empty(own_hi - own_lo, dtype=torch.float64).pin_memory().numpy()
     val = torch.empty(need_hi - need_lo, dtype=torch.float64).pin_memory().numpy()
-    out = torch.empty(own_hi - own_lo, dtype=torch.float64).pin_memory().numpy()
+    whole = (need_lo, need_hi) == (own_lo, own_hi)      # unpartitioned: the block IS the vector, values_ comes straight back into `val`
+    out = val if whole else torch.empty(own_hi - own_lo, dtype=torch.float64).pin_memory().numpy()
     if world > 1:
         mg.gather_values()                        # the host copy below must be the complete, current vector
     src[:] = fine.source_[own_lo:own_hi]
@@ -357,7 +358,8 @@ def main():
         fine.write_values_range(need_lo, val)     # H2D
         mg.vCycle(1)
         fine.read_values_range(own_lo, out)       # D2H straight into the pinned buffer
-        val[own_lo - need_lo: own_hi - need_lo] = out
+        if not whole:
+            val[own_lo - need_lo: own_hi - need_lo] = out
         return mg.residuals_[-1:]                 # D2H of the step's residual entry
 
     for _ in range(2):
