@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
 // Per-row arithmetic and lane mapping of k_sor_mc_flow / k_sor_mc_packed: same bits.
 // ------------------------------------------------------------------------------------------------
 template <int LPR, int ITER, int ROWS, bool PEER>
-__global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma_flow(const unsigned char* __restrict__ chunks, unsigned chunk_bytes, int W,
+__global__ void __launch_bounds__(kStreamThreads, 3) k_sor_mc_tma_flow(const unsigned char* __restrict__ chunks, unsigned chunk_bytes, int W,
                                                                     const int* __restrict__ phase_ptr, int pps, int iters, const double* __restrict__ b,
                                                                     double* xs, size_t stride, double omega, int* ctl, int stages, int dynamic,
                                                                     int* abort_flag, long long timeout_cycles, PeerSends peers) {
@@ -474,7 +474,7 @@ __device__ __forceinline__ void consumer_sum2(double& a, double& b, double* scra
 }
 
 template <int LPR, int ITER, int ROWS>
-__global__ void __launch_bounds__(kStreamThreads) k_spmv_tma(HybView A, const double* x, const double* __restrict__ b, double* y,
+__global__ void __launch_bounds__(kStreamThreads, 3) k_spmv_tma(HybView A, const double* x, const double* __restrict__ b, double* y,
                                                              const unsigned char* __restrict__ rowflag, int op, int mask_dirichlet, int mask_neumann,
                                                              double* __restrict__ partial, int row0, int nrows, int stages) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -530,6 +530,15 @@ __global__ void __launch_bounds__(kStreamThreads) k_spmv_tma(HybView A, const do
     for (int h = 0; h < ROWS; h++)
 #pragma unroll
       for (int t = 0; t < ITER; t++) xx[h][t] = c[h][t] >= 0 ? ldg_keep(x + c[h][t], keep) : 0.0;
+    // the epilogue's own operands (row flag, b_i or the old y_i) are fetched with the gathers, not after the reduction
+    int flag_[ROWS];
+    double aux_[ROWS];
+#pragma unroll
+    for (int h = 0; h < ROWS; h++) {
+      const bool lead = valid[h] && gl == 0;
+      flag_[h] = (lead && rowflag) ? rowflag[row[h]] : 0;
+      aux_[h] = !lead ? 0.0 : op == OP_RESID ? b[row[h]] : op == OP_PROLONG ? y[row[h]] : 0.0;
+    }
 #pragma unroll
     for (int h = 0; h < ROWS; h++) {
       double a = 0.0;
@@ -551,18 +560,18 @@ __global__ void __launch_bounds__(kStreamThreads) k_spmv_tma(HybView A, const do
 #pragma unroll
     for (int h = 0; h < ROWS; h++) {
       if (valid[h] && gl == 0) {
-        const int flag = rowflag ? rowflag[row[h]] : 0;
+        const int flag = flag_[h];
         if (op == OP_SPMV) {
           y[row[h]] = acc[h];
         } else if (op == OP_RESID) {
-          const double bi = b[row[h]];
+          const double bi = aux_[h];
           double t = __dsub_rn(bi, acc[h]);
           if (flag == 1) t = 0.0;
           if (y) y[row[h]] = t;
           num += fabs(t);
           den += fabs(bi);
         } else if (op == OP_PROLONG) {
-          if (!(mask_dirichlet && flag == 1)) y[row[h]] = __dadd_rn(y[row[h]], acc[h]);
+          if (!(mask_dirichlet && flag == 1)) y[row[h]] = __dadd_rn(aux_[h], acc[h]);
         } else {
           double t = acc[h];
           if (flag == 1) t = 0.0;
