@@ -1202,7 +1202,7 @@ __global__ void __launch_bounds__(kBlock) k_sor_mc2(HybView A, const int* __rest
 
 // ------------------------------------------------------------------------------------------------
 // Colour-major packed copy of the operator (fourth generation of the multicolour sweep).
-// ncu without cache flushing (profiles/r01_steady_state_4M.txt) showed the per-colour phases of k_sor_mc_all at
+// ncu without cache flushing (profiles/r01_steady_state_4M.txt) showed the per-colour phases of the natural-order sweep (one cooperative launch, rows of a colour through an index list; removed in round 2) at
 // 46 % of DRAM peak but 72 % of the L2 sector-read cap: a colour's rows are every ~15th row of the matrix, so
 // (a) the 448-byte row chunks are isolated DRAM bursts, (b) rows_list -> len -> chunk -> gather is a four-deep
 // chain of dependent loads, and (c) a CTA's 32 rows lie on a thin arc of one BFS ring, so hardly any gathered sector
@@ -2273,7 +2273,7 @@ void op_sor(Grid& g, int smoother) {
         const int iters = g.props.iters;
         const size_t stride = ((size_t)g.A + 63) / 64 * 64;
         if (g.xs.n < stride * (iters + 1)) g.xs.alloc(stride * (iters + 1));
-        if (g.A >= env_int("MMG_MC_TMAFLOW_MIN_ROWS", 100000) && env_int("MMG_MC_TMAFLOW", 1)) {     // the same sweep, operator fed through the TMA ring
+        if (g.A >= env_int("MMG_MC_TMAFLOW_MIN_ROWS", 2000) && env_int("MMG_MC_TMAFLOW", 1)) {     // the same sweep, operator fed through the TMA ring
           k_pipe_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, g.xs.p, stride, iters, g.A);
           MMG_CUDA(cudaGetLastError());
           ok = stream_sor_mc_flow(g, g.xs.p, stride, nullptr);
@@ -2658,7 +2658,7 @@ static bool dist_sor_peer(Solver& s, Grid& g, LevelDist& D) {
   k_peer_call_init<<<(g.A + kBlock - 1) / kBlock, kBlock, 0, g.stream>>>(g.rowflag.p, g.x.p, cur, nxt, stride, iters, D.peer_iters, g.A);
   MMG_CUDA(cudaGetLastError());
   bool tma_done = false;
-  if (g.mc_colour_ptr.back() >= env_int("MMG_MC_TMAFLOW_MIN_ROWS", 100000) && env_int("MMG_MC_TMAFLOW", 1)) {
+  if (g.mc_colour_ptr.back() >= env_int("MMG_MC_TMAFLOW_MIN_ROWS", 2000) && env_int("MMG_MC_TMAFLOW", 1)) {
     PeerSends peers{};
     peers.n = D.n_sends;
     for (int k = 0; k < D.n_sends; k++) {

@@ -722,7 +722,9 @@ bool stream_sor_mc_flow(Grid& g, double* xs, size_t stride, const PeerSends* pee
     size_t st = stride;
     double omega = g.props.omega;
     int* ctl = g.mc_ctl.p;
-    int stages = rs.stages, dynamic = env_int("MMG_TMA_DYNAMIC", 1);
+    // small levels: a colour is a handful of tiles, so a ticket per tile (two dependent atomics per phase and CTA) would be the
+    // critical path; tiles are dealt round-robin instead and the producer runs as far ahead as the ring allows
+    int stages = rs.stages, dynamic = env_int("MMG_TMAFLOW_DYNAMIC", swept >= 150000 ? 1 : 0);
     int* abortp = g.abort_flag.p;
     long long timeout = 6000000000ll;
     PeerSends ps{};

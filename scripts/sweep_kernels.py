@@ -39,6 +39,9 @@ for cfg in configs:
             parts.append("L%d " % l + " ".join("%s %.0fGB/s %.3fms" % (k, v["bytes"] / max(v["ms"], 1e-9) / 1e6, v["ms"] / cycles) for k, v in t.items() if v["ms"] > 0))
         tot = mg.timers(-1)
         coarse_sor = sum(mg.timers(l)["sor"]["ms"] for l in range(len(sides) - 2)) / cycles
+        if os.environ.get("SWEEP_ALL_LEVELS"):
+            print("   per level sor ms/cycle: " + " ".join("L%d(%d) %.3f" % (l, sides[l] ** 2, mg.timers(l)["sor"]["ms"] / cycles) for l in range(len(sides)))
+                  + " | spmv ms/cycle: " + " ".join("L%d %.3f" % (l, sum(mg.timers(l)[k]["ms"] for k in ("residual", "restrict", "prolong", "other")) / cycles) for l in range(len(sides))), flush=True)
         mg.enable_timers(False)
         print("CFG %s | %s %s | same_bits %s | %.3f ms/cycle launches/cycle %d | coarse-tail sor %.3f ms | %s" % (cfg, kern, spk, h == ref_hash, ms, sum(v["launches"] for v in tot.values()) // cycles, coarse_sor, " | ".join(parts)), flush=True)
     except Exception as e:
