@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 1: at-size parity tests + first sweep of the TMA-fed kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/r02_gpu1_smi.log 2>&1
 timeout 900 python -m pytest tests/test_gpu_at_size.py -x -q > gpurun_out/r02_atsize.log 2>&1; echo "atsize rc=$?"

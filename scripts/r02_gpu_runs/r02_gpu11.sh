@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests/test_gpu_operators.py tests/test_gpu_vcycle.py tests/test_gpu_fracstep.py -x -q -k "sor or history or neumann or mixed or ppe or time_step or quirk" > gpurun_out/r02_lexneu.log 2>&1; echo "tests rc=$?"
 tail -8 gpurun_out/r02_lexneu.log | cut -c1-250

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_at_size.py tests/test_gpu_vcycle.py -x -q -k "neumann or mixed or ppe" > gpurun_out/r02_lexneu3.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02_lexneu3.log | cut -c1-200
 for pipe in 1 0; do

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python scripts/sweep_kernels.py 2000 4 5 ';MMG_MC_TMAFLOW_MIN_ROWS=2000;MMG_MC_TMAFLOW_MIN_ROWS=2000,MMG_TMAFLOW_CTAS=2;MMG_MC_TMAFLOW_MIN_ROWS=2000,MMG_TMAFLOW_CTAS=1,MMG_TMAFLOW_SMEM_KB=60;MMG_MC_TMAFLOW_MIN_ROWS=10000,MMG_TMAFLOW_CTAS=2' > gpurun_out/r02_sweep9.log 2>&1; echo "sweep rc=$?"
 python - <<'PY'

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gputests.log 2>&1; echo "gputests rc=$?"
 tail -30 gpurun_out/r02_gputests.log | cut -c1-250

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests/test_gpu_at_size.py tests/test_gpu_facade.py tests/test_gpu_vcycle.py tests/test_gpu_fracstep.py tests/test_gpu_operators.py -x -q > gpurun_out/r02_gputests_b.log 2>&1; echo "gputests rc=$?"
 tail -5 gpurun_out/r02_gputests_b.log | cut -c1-250

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu captures of the round-2 kernels (one gpurun call; every ncu command follows a plain run of the same command).
 # Only text summaries (ncu -i ... --page raw, scripts/ncu_summary.py) and the report of the dominant kernel travel back.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 T=/tmp/ncu_r02; mkdir -p $T
 NCU="ncu --set full --clock-control none"
