@@ -156,9 +156,9 @@ def test_fast_multicolour_sweep_variants_are_bit_identical(libmmg, monkeypatch):
     Rows of one colour are independent, so all must produce the same bits -- a stale read across a barrier shows up here."""
     from meshlessmultigridpoisson_b200.problems import make_hierarchy
 
-    knobs = ("MMG_MC_PACKED", "MMG_MC_SMALL", "MMG_MC_FLOW", "MMG_MC_TMA", "MMG_MC_RESIDENT", "MMG_MC_FLOW_MAX_ROWS", "MMG_TMA_ROWS", "MMG_TMA_DYNAMIC", "MMG_MC_TMAFLOW_MIN_ROWS")
+    knobs = ("MMG_MC_PACKED", "MMG_MC_SMALL", "MMG_MC_FLOW", "MMG_MC_TMA", "MMG_MC_RESIDENT", "MMG_MC_FLOW_MAX_ROWS", "MMG_TMA_ROWS", "MMG_TMA_DYNAMIC", "MMG_MC_TMAFLOW_MIN_ROWS", "MMG_MC_TMAFLOW")
     results = []
-    for env in ({"MMG_MC_PACKED": "0"}, {}, {"MMG_MC_TMAFLOW_MIN_ROWS": "0"}, {"MMG_MC_FLOW": "0"}, {"MMG_MC_FLOW": "0", "MMG_TMA_ROWS": "1", "MMG_TMA_DYNAMIC": "0"},
+    for env in ({"MMG_MC_PACKED": "0"}, {}, {"MMG_MC_TMAFLOW_MIN_ROWS": "0"}, {"MMG_MC_TMAFLOW": "0"}, {"MMG_MC_FLOW": "0"}, {"MMG_MC_FLOW": "0", "MMG_TMA_ROWS": "1", "MMG_TMA_DYNAMIC": "0"},
                 {"MMG_MC_FLOW": "0", "MMG_MC_TMA": "0"}, {"MMG_MC_SMALL": "0"}, {"MMG_MC_RESIDENT": "0"}, {"MMG_MC_RESIDENT": "0", "MMG_MC_SMALL": "0"}):
         for k in knobs:
             monkeypatch.delenv(k, raising=False)
