@@ -110,10 +110,10 @@ def test_fast_multicolour_sweep_at_size_p6(h250k_p6, monkeypatch):
         assert H.rel_err(g.values_, lv.values) < 1e-12, capi.last_kernel(0)
 
 
-@pytest.mark.parametrize("arith", ["reference_order", "fast"])
-def test_residual_restrict_prolong_at_size(h250k, monkeypatch, arith):
-    """k_spmv2 / the TMA-fed SpMV on >= 200k rows (fast) and k_spmv_exact (reference order)"""
-    gpu, ref = h250k
+@pytest.mark.parametrize("arith,poly", [("reference_order", 4), ("fast", 4), ("fast", 6)])
+def test_residual_restrict_prolong_at_size(h250k, h250k_p6, monkeypatch, arith, poly):
+    """k_spmv2 / the TMA-fed SpMV on >= 200k rows (fast; polyDeg 4: 8 lanes per row, polyDeg 6: 16) and k_spmv_exact (reference order)"""
+    gpu, ref = h250k if poly == 4 else h250k_p6
     clean_env(monkeypatch)
     exact = arith == "reference_order"
     gpu.set_arithmetic(capi.ARITH_REFERENCE_ORDER if exact else capi.ARITH_FAST)
@@ -129,7 +129,7 @@ def test_residual_restrict_prolong_at_size(h250k, monkeypatch, arith):
     close(g.residual(), fine.residual())
     assert abs(gpu.residual() - ref.residual()) <= 1e-12 * abs(ref.residual())
     if not exact:
-        assert capi.last_kernel(1).startswith(("k_spmv2<8,5", "k_spmv_tma<")), capi.last_kernel(1)
+        assert capi.last_kernel(1).startswith("k_spmv_tma<8,5" if poly == 4 else "k_spmv_tma<16,5"), capi.last_kernel(1)
     coarse = ref.level(L - 1)
     r = fine.residual()
     src = coarse.source
