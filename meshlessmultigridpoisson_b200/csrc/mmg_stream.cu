@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
                                                                const int* __restrict__ phase_ptr, int pps, int bnd_phase, int iters,
                                                                const double* __restrict__ b, double* x, double omega, int* ctl, int stages,
                                                                int dynamic, int* abort_flag, long long timeout_cycles, int debug_flags, HybView A,
-                                                               RegRow reg) {
+                                                               RegRow reg, int static_8ths) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red_scratch[kConsumerWarps];
   constexpr int GPW = 32 / LPR;
@@ -154,15 +154,23 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
     int s = 0;
     unsigned par = 0;
     int phase = 0;
-    int ticket = dynamic ? atomicAdd(&tickets[0], 1) : (int)blockIdx.x;
+    // Tiles of a phase: every CTA first takes a contiguous share of `share` tiles (neighbours along the Z-curve, so consecutive
+    // tiles of a CTA re-use each other's x lines in L1), the rest is dealt by tickets to even out the end of the phase.
+    const int G = (int)gridDim.x;
+    int j = 0, ticket = -1;
     for (;;) {
-      int t = ticket, first = 0, count = 0;
-      while (phase < nphases) {                          // the ticket is stale once its phase has no tiles left
+      int t = 0, first = 0, count = 0, share = 0;
+      while (phase < nphases) {
         const int c = phase % pps;
         first = phase_ptr[c];
         count = phase_ptr[c + 1] - first;
-        if (t < (count + TR - 1) / TR) break;
-        if (++phase < nphases) t = dynamic ? atomicAdd(&tickets[phase], 1) : (int)blockIdx.x;
+        const int tiles = (count + TR - 1) / TR;
+        share = dynamic ? (int)(((long long)tiles * static_8ths) / (8ll * G)) : 0;
+        if (j < share) { t = (int)blockIdx.x * share + j; break; }
+        if (ticket < 0) ticket = dynamic ? atomicAdd(&tickets[phase], 1) : (int)blockIdx.x;
+        t = G * share + ticket;
+        if (t < tiles) break;                            // otherwise the ticket is stale: the phase has no tiles left
+        ++phase; j = 0; ticket = -1;
       }
       mbar_wait(&C->empty[s], par ^ 1u);
       if (phase >= nphases) {                            // terminator
@@ -170,7 +178,8 @@ __global__ void __launch_bounds__(kStreamThreads) k_sor_mc_tma(const unsigned ch
         mbar_arrive(&C->full[s]);
         return;
       }
-      ticket = dynamic ? atomicAdd(&tickets[phase], 1) : t + (int)gridDim.x;     // in flight while this tile is issued
+      if (j < share) { if (++j == share) ticket = dynamic ? atomicAdd(&tickets[phase], 1) : (int)blockIdx.x; }
+      else ticket = dynamic ? atomicAdd(&tickets[phase], 1) : ticket + G;       // in flight while this tile is issued
       const int r0 = first + t * TR;
       const int n = min(TR, count - t * TR);
       C->phase[s] = phase; C->row0[s] = r0; C->nrows[s] = n;
@@ -675,7 +684,11 @@ bool stream_sor_mc(Grid& g) {
     int debug_flags = env_int("MMG_TMA_DEBUG", 0);      // timing decomposition only (1: no colour barrier, 2: no gathers): results invalid
     HybView A = L.view();
     RegRow reg{L.reg_col.p, L.reg_val.p, L.reg_len, L.reg_row, L.reg_diag, g.mc_reg_partial.p};
-    void* args[] = {&chunks, &cb, &W, &cp, &ppsv, &bnd_phase, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &debug_flags, &A, &reg};
+    // contiguous share of a phase's tiles per CTA before the ticket-dealt rest, in 1/8 of the even share (profiles/r02_static_share.txt:
+    // 4836 -> 4920 GB/s at n=37, 4570 -> 4610 at n=70 with the whole even share static; handing the shares of the CTAs that share
+    // an SM to neighbours along the curve as well changes nothing, r02_static_share3.txt)
+    int static_8ths = std::max(0, std::min(8, env_int("MMG_TMA_STATIC_8THS", 8)));
+    void* args[] = {&chunks, &cb, &W, &cp, &ppsv, &bnd_phase, &iters, &b, &x, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &debug_flags, &A, &reg, &static_8ths};
     note_kernel(g, "k_sor_mc_tma", LPR, ITER, rows_used);
     MMG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(blocks), dim3(kStreamThreads), args, rs.smem, g.stream));
   });
