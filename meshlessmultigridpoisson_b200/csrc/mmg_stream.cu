@@ -328,7 +328,7 @@ template <int LPR, int ITER, int ROWS, bool PEER>
 __global__ void __launch_bounds__(kStreamThreads, 3) k_sor_mc_tma_flow(const unsigned char* __restrict__ chunks, unsigned chunk_bytes, int W,
                                                                     const int* __restrict__ phase_ptr, int pps, int iters, const double* __restrict__ b,
                                                                     double* xs, size_t stride, double omega, int* ctl, int stages, int dynamic,
-                                                                    int* abort_flag, long long timeout_cycles, PeerSends peers) {
+                                                                    int* abort_flag, long long timeout_cycles, PeerSends peers, int l1_first) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int GPW = 32 / LPR;
   constexpr int TR = kConsumerWarps * GPW * ROWS;
@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(kStreamThreads, 3) k_sor_mc_tma_flow(const uns
   const int gl = lane % LPR, q = lane / LPR;
   const unsigned gmask = group_mask<LPR>(lane);
   const double om1 = 1 - omega;
+  const unsigned long long keep = policy_evict_last();
   const long long t_start = clock64();
   int s = 0;
   unsigned par = 0;
@@ -407,7 +408,9 @@ __global__ void __launch_bounds__(kStreamThreads, 3) k_sor_mc_tma_flow(const uns
           c[h][t] = raw & kColMask;
           if (raw < 0) newer |= 1u << (h * ITER + t);
           const double* src = (raw < 0 ? xnew : xold) + c[h][t];
-          xx[h][t] = PEER ? ld_relaxed_sys(src) : ld_relaxed(src);
+          // First probe through L1: within one launch every entry of a version goes sentinel -> value exactly once, so a cached
+          // line can hold a stale SENTINEL (then the strong poll below fetches the value from L2) but never a stale value.
+          xx[h][t] = l1_first ? ldg_keep(src, keep) : PEER ? ld_relaxed_sys(src) : ld_relaxed(src);
           if (is_sentinel(xx[h][t])) pend |= 1u << (h * ITER + t);
         } else xx[h][t] = 0.0;
       }
@@ -742,7 +745,8 @@ bool stream_sor_mc_flow(Grid& g, double* xs, size_t stride, const PeerSends* pee
     long long timeout = 6000000000ll;
     PeerSends ps{};
     if (peers) ps = *peers;
-    void* args[] = {&chunks, &cb, &W, &cp, &ppsv, &iters, &b, &xs, &st, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &ps};
+    int l1_first = env_int("MMG_TMAFLOW_L1", 1);
+    void* args[] = {&chunks, &cb, &W, &cp, &ppsv, &iters, &b, &xs, &st, &omega, &ctl, &stages, &dynamic, &abortp, &timeout, &ps, &l1_first};
     note_kernel(g, peers ? "k_sor_mc_tma_flow_peer" : "k_sor_mc_tma_flow", LPR, ITER, rows_used);
     MMG_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kStreamThreads), args, rs.smem, g.stream));
   });
