@@ -41,3 +41,19 @@ def test_reference_arm_prints_one_line_on_rank0_only():
     assert line["solve"]["converged"] and line["solve"]["final_residual"] < 1e-8 and line["solve"]["cycles"] >= 1
     assert "100x100" in line["config"]["workload"] and "lexicographic" in line["config"]["smoother"]
     assert abs(line["ms_per_step"] * line["value"] - 1e3) < 1e-6
+
+
+def test_golden_histories_of_the_bench_workload_are_committed():
+    # the in-run check of bench.py: the first cycles of the 2000^2 workload from the CPU oracle alone, polyDeg 4 and 6
+    for poly in (4, 6):
+        for key in ("lexicographic_omega1.4", "multicolour_omega0.8"):
+            h = bench.golden_history(2000, poly, key)
+            assert h is not None and len(h) >= 6 and h[0] == 1.0
+            assert all(b < a for a, b in zip(h, h[1:]))               # both smoothers contract on this workload
+    assert bench.golden_history(2000, 5, "multicolour_omega0.8") is None   # no fixture: bench reports check = null, it does not guess
+
+
+def test_ncu_traffic_lookup_is_keyed_on_kernel_and_workload():
+    t = bench.ncu_traffic("k_sor_mc_tma<8,5,2>", 2000, 4)
+    assert t is not None and 0.9 < t / 9.44e9 < 1.1                  # measured DRAM bytes per launch against the algorithmic 9.44 GB
+    assert bench.ncu_traffic("k_sor_mc_tma<8,5,2>", 1000, 4) is None and bench.ncu_traffic("no_such_kernel", 2000, 4) is None
