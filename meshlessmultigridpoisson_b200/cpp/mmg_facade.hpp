@@ -13,6 +13,7 @@
 #include <cmath>
 #include <stdexcept>
 #include <fstream>
+#include <iostream>
 #include <string>
 #include <tuple>
 #include <utility>
@@ -214,6 +215,69 @@ class Grid {
   int getPolyDeg() const { return properties_.polyDeg; }
   mmg_grid* handle() { return h_; }
 
+  // ---- per-point queries of grid.h:60-72.  The bulk assembly never goes through them (one launch builds every row); they are
+  // here for callers that inspect single stencils.  Weights come back as (weights, neighbour ids) like in the reference, the
+  // weight vector as DenseVector (Eigen::VectorXd with Eigen, std::vector<double> without).
+  std::vector<Point> pointIDs_to_vector(const std::vector<int>& pointIDs) const {          // grid.cpp:206-212
+    std::vector<Point> pts;
+    for (size_t i = 0; i < pointIDs.size(); i++) pts.push_back(points_.at(pointIDs.at(i)));
+    return pts;
+  }
+  std::vector<int> kNearestNeighbors(Point point, bool neumannFlag, bool pointBCFlag, int k) {   // grid.cpp:216-260
+    sync_flags();
+    const double x = std::get<0>(point), y = std::get<1>(point);
+    const int flag = pointBCFlag ? 1 : 0;
+    std::vector<int> out(k);
+    check(mmg_grid_knn(h_, 1, &x, &y, &flag, neumannFlag ? 1 : 0, k, out.data()), "Grid::kNearestNeighbors");
+    return out;
+  }
+  std::vector<int> kNearestNeighbors(int pointNumber, bool neumannFlag, int k) {            // grid.cpp:213-215
+    return kNearestNeighbors(points_.at(pointNumber), neumannFlag, bcFlags().at(pointNumber) != 0, k);
+  }
+  std::pair<DenseVector, std::vector<int>> laplaceWeights(int pointID) { return weights_of(MMG_MAT_LAPLACE, pointID, "Grid::laplaceWeights"); }   // grid.cpp:381-424
+  std::pair<DenseVector, std::vector<int>> derivx_weights(int pointID) { return weights_of(MMG_MAT_DERIVX, pointID, "Grid::derivx_weights"); }    // grid.cpp:304-342
+  std::pair<DenseVector, std::vector<int>> derivy_weights(int pointID) { return weights_of(MMG_MAT_DERIVY, pointID, "Grid::derivy_weights"); }    // grid.cpp:343-380
+  std::pair<DenseVector, std::vector<int>> pointInterpWeights(Point point, int polyDeg) {   // grid.cpp:687-712
+    sync_flags();
+    const int n = (int)(2.5 * (polyDeg + 1) * (polyDeg + 2) / 2);                            // grid.cpp:266-267
+    const double x = std::get<0>(point), y = std::get<1>(point);
+    std::vector<double> w(n);
+    std::vector<int> nb(n);
+    check(mmg_grid_point_interp_weights(h_, 1, &x, &y, polyDeg, w.data(), nb.data()), "Grid::pointInterpWeights");
+    return std::make_pair(to_dense(w), nb);
+  }
+  // public data members of grid.h:23-38 that live on the device: fetched on request
+  std::vector<int> bcFlags() {                                                              // bcFlags_
+    std::vector<int> f(laplaceMatSize_);
+    check(mmg_grid_get_bcflags(h_, f.data()), "bcFlags_");
+    return f;
+  }
+  std::vector<Point> normalVecs() {                                                         // normalVecs_ (after build_normal_vecs)
+    std::vector<double> nx(laplaceMatSize_), ny(laplaceMatSize_);
+    check(mmg_grid_get_normals(h_, nx.data(), ny.data()), "normalVecs_");
+    std::vector<Point> out(laplaceMatSize_);
+    for (int i = 0; i < laplaceMatSize_; i++) out[i] = Point(nx[i], ny[i], 0.0);
+    return out;
+  }
+  DenseVector diags() {                                                                     // diags (after build_laplacian)
+    std::vector<double> d(values_->rows());
+    check(mmg_grid_get_diags(h_, d.data()), "diags");
+    return to_dense(d);
+  }
+  void setNeumannFlag() {                                                                   // grid.cpp:52-60
+    neumannFlag_ = false;
+    for (const Boundary& b : boundaries_) if (b.type == MMG_BC_NEUMANN) neumannFlag_ = true;
+  }
+  void print_bc_values() {                                                                  // grid.cpp:165-171
+    for (const Boundary& b : boundaries_)
+      for (size_t j = 0; j < b.bcPoints.size(); j++) std::cout << "bc value: " << b.values.at(j) << std::endl;
+  }
+  void print_bc_values(const DenseVector& vec) {                                            // grid.cpp:156-164: Dirichlet boundaries only
+    for (const Boundary& b : boundaries_)
+      if (b.type == MMG_BC_DIRICHLET)
+        for (size_t j = 0; j < b.bcPoints.size(); j++) std::cout << "bc value: " << entry(vec, b.bcPoints.at(j)) << std::endl;
+  }
+
  protected:
   void push_all() { sync_flags(); push(); }
 
@@ -221,6 +285,28 @@ class Grid {
   template <class GridT> friend class BasicMultigrid;
   void sync_flags() { check(mmg_grid_set_implicit(h_, implicitFlag_), "implicitFlag_"); }
   void push() { values_->push(); source_.push(); }
+#ifdef MMG_FACADE_HAVE_EIGEN
+  static double entry(const Eigen::VectorXd& v, int i) { return v(i); }
+#else
+  static double entry(const std::vector<double>& v, int i) { return v.at(i); }
+#endif
+  static DenseVector to_dense(const std::vector<double>& v) {
+#ifdef MMG_FACADE_HAVE_EIGEN
+    Eigen::VectorXd out((int)v.size());
+    for (int i = 0; i < (int)v.size(); i++) out(i) = v[i];
+    return out;
+#else
+    return v;
+#endif
+  }
+  std::pair<DenseVector, std::vector<int>> weights_of(int which, int pointID, const char* what) {
+    sync_flags();
+    const int n = properties_.stencilSize;
+    std::vector<double> w(n);
+    std::vector<int> nb(n);
+    check(mmg_grid_weights(h_, which, 1, &pointID, w.data(), nb.data()), what);
+    return std::make_pair(to_dense(w), nb);
+  }
   void refresh() {   // after a reordering the host-side copies of points_/boundaries_ follow the device
     const int n = laplaceMatSize_;
     std::vector<double> x(n), y(n);

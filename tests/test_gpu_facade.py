@@ -87,3 +87,42 @@ def test_ownership_rules_of_add_grid(libmmg):
     w = make_hierarchy([13, 25], "dirichlet", 3).grid(-1)      # the solver object is unreachable except through the wrapper
     import gc; gc.collect()
     assert np.isfinite(w.values_).all() and w.getSize() == 625
+
+
+def test_per_point_queries_of_the_facade_match_the_ctypes_mirror(libmmg, tmp_path):
+    """Grid::kNearestNeighbors / laplaceWeights / derivx_weights / derivy_weights / pointInterpWeights / pointIDs_to_vector / diags
+    of the C++ facade (grid.h:60-72) against the same C-ABI entries called through capi.py on an identically built level."""
+    from meshlessmultigridpoisson_b200 import capi
+    from meshlessmultigridpoisson_b200.problems import make_grid, stencil_size
+
+    cpp = os.path.join(ROOT, "meshlessmultigridpoisson_b200", "cpp")
+    subprocess.check_call(["make", "-s", "-C", cpp])
+    poly, s = 4, 24
+    x, y = jittered_square(s, seed=7)
+    fn = str(tmp_path / "level.msh")
+    write_msh_nodes(fn, x, y)
+    ids = [0, 5, 100, 333, s * s - 1]                      # boundary and interior nodes (numbering after the reordering)
+    out = subprocess.check_output([os.path.join(cpp, "query_stencil"), str(poly), fn, *map(str, ids)], text=True).strip().split("\n")
+    rec = {}
+    for line in out:
+        t = line.split()
+        rec[(t[0], int(t[1]))] = t[2:]
+    g = make_grid("dirichlet", x, y, poly)
+    n = stencil_size(poly)
+    px, py = g.points_
+    flags = g.bcFlags_
+    for i in ids:
+        knn = g.kNearestNeighbors(px[i], py[i], n, neumann=False, q_bcflag=[int(flags[i] != 0)])[0]
+        assert [int(v) for v in rec[("knn", i)]] == knn.tolist()
+        for tag, which in (("laplace", capi.MAT_LAPLACE), ("derivx", capi.MAT_DERIVX), ("derivy", capi.MAT_DERIVY)):
+            w, nb = g.weights(which, [i], n)
+            got = [t.split(":") for t in rec[(tag, i)]]
+            assert [int(a) for a, _ in got] == nb[0].tolist()
+            assert np.array_equal(np.array([float(b) for _, b in got]), w[0])          # 17 digits round-trip: identical
+        j = int(knn[1])
+        w, nb = g.pointInterpWeights(0.5 * (px[i] + px[j]), 0.5 * (py[i] + py[j]), poly)
+        got = [t.split(":") for t in rec[("interp", i)]]
+        assert [int(a) for a, _ in got] == nb[0].tolist()
+        assert np.array_equal(np.array([float(b) for _, b in got]), w[0])
+        assert abs(sum(float(b) for _, b in got) - 1.0) < 1e-9                          # interpolation weights sum to one
+        assert float(rec[("diag", i)][0]) == g.diags[i]
