@@ -444,8 +444,23 @@ class BasicMultigrid {
   }
   void setSmoother(int smoother) { check(mmg_solver_set_smoother(h_, smoother), "setSmoother"); }
   mmg_solver* handle() { return h_; }
+  void sortGridsBySize() { std::sort(grids_.begin(), grids_.end()); }                       // multigrid.cpp:116-122
+  // restrictionMatrices_[level] / prolongMatrices_[level] (multigrid.h:8-9) live on the device; a host copy in CSR on request.
+  // Levels as in the reference: restriction `level` maps grid level -> level-1 (level >= 1), prolongation `level` maps
+  // grid level -> level+1 (level < numGrids-1).
+  struct InterpCsr { int rows = 0, cols = 0; std::vector<int> ptr, idx; std::vector<double> val; };
+  InterpCsr restrictionMatrix(int level) { return interp(MMG_MAT_RESTRICT, level); }
+  InterpCsr prolongMatrix(int level) { return interp(MMG_MAT_PROLONG, level); }
 
  private:
+  InterpCsr interp(int which, int level) {
+    InterpCsr m;
+    int64_t nnz = 0;
+    check(mmg_solver_interp_nnz(h_, which, level, &m.rows, &m.cols, &nnz), "restrictionMatrices_/prolongMatrices_");
+    m.ptr.resize(m.rows + 1); m.idx.resize((size_t)nnz); m.val.resize((size_t)nnz);
+    check(mmg_solver_get_interp_csr(h_, which, level, m.ptr.data(), m.idx.data(), m.val.data()), "restrictionMatrices_/prolongMatrices_");
+    return m;
+  }
   mmg_solver* h_ = nullptr;
 };
 

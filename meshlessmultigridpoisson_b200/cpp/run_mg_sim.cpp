@@ -69,6 +69,20 @@ int main(int argc, char** argv) {
     for (int i = 0; i < fine->laplaceMatSize_; i++)   // calc_l1_error, testing_functions.cpp:3-16
       err += std::fabs((*fine->values_)(i) - std::sin(pi * std::get<0>(fine->points_[i])) * std::sin(pi * std::get<1>(fine->points_[i])));
     printf("l1_error %.17g\n", err / fine->laplaceMatSize_);
+    if (getenv("MMG_PRINT_INTERP")) {                 // restrictionMatrices_ / prolongMatrices_: shapes, entries, largest |row sum - 1|
+      for (int l = 0; l < numGrids; l++)
+        for (int which = 0; which < 2; which++) {
+          if ((which == 0 && l == 0) || (which == 1 && l == numGrids - 1)) continue;
+          const Multigrid::InterpCsr m = which == 0 ? mg.restrictionMatrix(l) : mg.prolongMatrix(l);
+          double dev = 0;
+          for (int r = 0; r < m.rows; r++) {
+            double sum = 0;
+            for (int k = m.ptr[r]; k < m.ptr[r + 1]; k++) sum += m.val[k];
+            dev = std::fmax(dev, std::fabs(sum - 1.0));
+          }
+          printf("interp %s %d %d %d %d %.3g\n", which == 0 ? "R" : "P", l, m.rows, m.cols, m.ptr[m.rows], dev);
+        }
+    }
     if (const char* dir = getenv("MMG_OUT_DIR")) {    // write_mg_resid + write_temp_contour, testing_functions.cpp:346-349
       const std::string extension = std::to_string(numGrids) + "grid__L=" + std::to_string(poly_deg);
       write_mg_resid(mg, std::string(dir) + "/", extension);

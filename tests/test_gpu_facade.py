@@ -21,12 +21,20 @@ def test_cpp_driver_matches_python_driver_bit_for_bit(libmmg, tmp_path):
         fn = str(tmp_path / ("l%d.msh" % l))
         write_msh_nodes(fn, x, y)
         files.append(fn)
-    out = subprocess.check_output([os.path.join(cpp, "run_mg_sim"), "12", "4", *files], text=True, env=dict(os.environ, MMG_OUT_DIR=str(tmp_path))).split("\n")
+    out = subprocess.check_output([os.path.join(cpp, "run_mg_sim"), "12", "4", *files], text=True, env=dict(os.environ, MMG_OUT_DIR=str(tmp_path), MMG_PRINT_INTERP="1")).split("\n")
     hist = np.array([float(t) for t in out[:12]])
     err = float(out[12].split()[1])
     mg = make_hierarchy(sizes, "dirichlet", 4)
     mg.vCycle(12)
     assert np.array_equal(hist, mg.residuals_)          # same library, same device-built operators: identical
+    # restrictionMatrices_ / prolongMatrices_ fetched through the facade: shapes of multigrid.cpp:17-48, n = 37 entries per row
+    # (the finest grid's polyDeg, multigrid.cpp:22,25), interpolation weights summing to one
+    interp = {(t[1], int(t[2])): (int(t[3]), int(t[4]), int(t[5]), float(t[6])) for t in (l.split() for l in out if l.startswith("interp "))}
+    n2 = [s_ * s_ for s_ in sizes]
+    assert set(interp) == {("R", 1), ("R", 2), ("P", 0), ("P", 1)}
+    for l in (1, 2):
+        assert interp[("R", l)][:3] == (n2[l - 1], n2[l], 37 * n2[l - 1]) and interp[("R", l)][3] < 1e-9
+        assert interp[("P", l - 1)][:3] == (n2[l], n2[l - 1], 37 * n2[l]) and interp[("P", l - 1)][3] < 1e-9
     assert hist[-1] < 2e-3 * hist[0] and err < 1e-3
     # the reference's text writers (write_mg_resid / write_temp_contour): one value per line, 6 significant digits
     resid = np.loadtxt(tmp_path / "resid_3grid__L=4.txt")
