@@ -11,6 +11,8 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <fstream>
 #include <iostream>
@@ -481,6 +483,26 @@ using mmgf::Grid;
 using mmgf::BasicMultigrid;
 // ---- the reference's text writers, same file names and number format (std::ofstream default: 6 significant digits, one
 // value per line), so the author's plotting scripts read the files unchanged
+// Gmsh v2 ASCII $Nodes block -> points, what pointsFromMshFile does in the reference (fileReadingFunctions.cpp:6-32); unlike the
+// reference a missing file or a malformed block is an exception, not an endless loop
+inline std::vector<mmgf::Point> pointsFromMshFile(const char* fname) {
+  std::vector<mmgf::Point> points;
+  FILE* f = std::fopen(fname, "r");
+  if (!f) throw std::runtime_error(std::string("cannot open ") + fname);
+  char tok[64];
+  bool found = false;
+  while (std::fscanf(f, "%63s ", tok) == 1) if (std::strcmp(tok, "$Nodes") == 0) { found = true; break; }
+  int nv = 0;
+  if (!found || std::fscanf(f, "%i ", &nv) != 1) { std::fclose(f); throw std::runtime_error(std::string("no $Nodes block in ") + fname); }
+  for (int iv = 0; iv < nv; iv++) {
+    int id;
+    double x, y, z;
+    if (std::fscanf(f, "%i %lf %lf %lf ", &id, &x, &y, &z) != 4) { std::fclose(f); throw std::runtime_error(std::string("bad node line in ") + fname); }
+    points.push_back(mmgf::Point(x, y, z));
+  }
+  std::fclose(f);
+  return points;
+}
 inline void writeVectorToTxt(const std::vector<double>& vec, const char* filename) {      // fileReadingFunctions.cpp:70-79
   std::ofstream file;
   file.open(filename);

@@ -11,23 +11,7 @@
 #include "mmg_facade.hpp"
 
 using namespace mmgf;
-
-static std::vector<Point> pointsFromMshFile(const char* fname) {     // fileReadingFunctions.cpp:6-32
-  std::vector<Point> points;
-  FILE* f = fopen(fname, "r");
-  if (!f) throw std::runtime_error(std::string("cannot open ") + fname);
-  char tok[64];
-  while (fscanf(f, "%63s ", tok) == 1 && strcmp(tok, "$Nodes") != 0) {}
-  int nv = 0;
-  if (fscanf(f, "%i ", &nv) != 1) throw std::runtime_error("bad $Nodes block");
-  for (int iv = 0; iv < nv; iv++) {
-    int id; double x, y, z;
-    if (fscanf(f, "%i %lf %lf %lf ", &id, &x, &y, &z) != 4) throw std::runtime_error("bad node line");
-    points.push_back(Point(x, y, z));
-  }
-  fclose(f);
-  return points;
-}
+using namespace mmgf_io;
 
 static double at(const DenseVector& v, int i) {
 #ifdef MMG_FACADE_HAVE_EIGEN

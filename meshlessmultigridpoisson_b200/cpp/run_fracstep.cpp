@@ -19,23 +19,6 @@ using namespace mmgf;
 using namespace mmgf_io;
 static const double PI = 3.141592653589793238462643383279502884;   // EIGEN_PI as a double
 
-static std::vector<Point> pointsFromMshFile(const char* fname) {
-  std::vector<Point> points;
-  FILE* f = fopen(fname, "r");
-  if (!f) throw std::runtime_error(std::string("cannot open ") + fname);
-  char tok[64];
-  while (fscanf(f, "%63s ", tok) == 1 && strcmp(tok, "$Nodes") != 0) {}
-  int nv = 0;
-  if (fscanf(f, "%i ", &nv) != 1) throw std::runtime_error("bad $Nodes block");
-  for (int iv = 0; iv < nv; iv++) {
-    int id; double x, y, z;
-    if (fscanf(f, "%i %lf %lf %lf ", &id, &x, &y, &z) != 4) throw std::runtime_error("bad node line");
-    points.push_back(Point(x, y, z));
-  }
-  fclose(f);
-  return points;
-}
-
 static FractionalStepGrid* genFractionalStepGrid(const char* filename, GridProperties props, double dt, double mu, double rho, double ppe_conv, std::string coarse) {
   std::vector<Point> points = pointsFromMshFile(filename);
   std::vector<int> bPts;
