@@ -17,10 +17,14 @@ Reported on ONE JSON line:
   lexicographic        the reference-faithful mode (dependency-DAG lexicographic SOR, reference-order row sums), reported separately
   solve                cycles and seconds to reduce |b-Ax|_1/|b|_1 below 1e-8 (loop shape of FractionalStepSim.cpp:139-142)
   roofline             the dominant kernel (finest-level SOR sweep): algorithmic bytes / CUDA-event time vs measured HBM peak
-  cpu_baseline         the CPU oracle (restated reference) on a bounded sample of the same workload, single thread like the reference
+  cpu_baseline         the reference's own V-cycle on the host (below) on a bounded sample of the same workload, single thread like the reference
 
-`--impl reference` times only the CPU oracle (all host threads for set-up, one thread for the V-cycle — the reference is
-strictly serial) and prints the same line with "impl": "reference".
+`--impl reference` times the reference's own CPU implementation of the path on the stated workload: Multigrid::vCycle /
+Grid::sor / Grid::residual from the reference's grid.cpp and multigrid.cpp as compiled into oracle/_ref/libref.so (kind
+"reference"), one thread because the reference is strictly serial.  Its operators come from the CPU oracle's set-up on all host
+threads, untimed -- bit-identical to the reference's own assembly, whose brute-force kNN is O(N^2) and would not finish at this
+size.  Without libref.so (or with --ref-port) the oracle's restatement of the V-cycle is timed instead (kind "port").  The line
+carries "impl": "reference".
 """
 import argparse
 import json
@@ -150,10 +154,16 @@ def run_cpu_oracle(side, levels_below, fine_poly, cycles, threads_setup):
     sides = level_sides(side)
     t0 = time.time()
     mg = oracle.make_hierarchy(sides, kind=oracle.KIND_DIRICHLET, fine_poly=fine_poly)
+    kind = "port"
+    try:                                          # the cycles run the reference's own code when oracle/_ref/libref.so is there (see reference_arm)
+        if oracle.ReferenceHierarchy.available():
+            mg, kind = oracle.ReferenceHierarchy.from_oracle(mg), "reference"
+    except (OSError, AttributeError, oracle.OracleError):
+        kind = "port"
     setup_s = time.time() - t0
     mg.vcycle(1)                                  # warm caches / page in
     secs = mg.time_vcycles(cycles)
-    return dict(sides=sides, setup_s=setup_s, s_per_cycle=secs / cycles, history=mg.history().tolist())
+    return dict(sides=sides, setup_s=setup_s, s_per_cycle=secs / cycles, history=mg.history().tolist(), kind=kind)
 
 
 def reference_arm(args):
@@ -173,6 +183,15 @@ def reference_arm(args):
     sides = level_sides(args.side, args.levels)
     t0 = time.time()
     mg = oracle.make_hierarchy(sides, kind=oracle.KIND_DIRICHLET, fine_poly=args.fine_poly)
+    kind = "port"
+    if oracle.ReferenceHierarchy.available() and not args.ref_port:
+        # oracle/_ref/libref.so = the reference's own grid.cpp / multigrid.cpp compiled where they lie: the cycles that are timed run
+        # the reference's code; only the set-up (brute-force kNN, O(N^2) in the reference) is the oracle's, whose matrices are pinned
+        # bit-identical to the reference's (tests/test_oracle_cpu.py)
+        try:
+            mg, kind = oracle.ReferenceHierarchy.from_oracle(mg), "reference"      # the oracle hierarchy is released with the last reference to it
+        except (OSError, AttributeError, oracle.OracleError) as e:               # a libref.so that does not load or predates the raw entry points
+            print("bench.py: reference objects unavailable (%s); timing the oracle port" % e, file=sys.stderr)
     setup_s = time.time() - t0
     per_cycle, t_solve0 = [], time.perf_counter()
     budget_s = max(0.0, args.ref_budget_s - setup_s)
@@ -190,10 +209,13 @@ def reference_arm(args):
     v = 1.0 / s_step
     hist = mg.history()
     rate = float((hist[min(len(hist) - 1, 20)] / hist[min(len(hist) - 1, 5)]) ** (1.0 / max(1, min(len(hist) - 1, 20) - min(len(hist) - 1, 5)))) if len(hist) > 6 else None
-    sample = ("CPU oracle (the reference's grid.cpp / multigrid.cpp restated, pinned bit-identical to the reference sources; g++ -O2 "
-              "-ffp-contract=off), MEASURED on the stated %dx%d hierarchy %s: lexicographic SOR omega=1.4, V-cycle loop on 1 thread because the "
+    what = ("the reference's OWN Multigrid::vCycle / Grid::sor / Grid::residual (oracle/_ref/libref.so: its grid.cpp and multigrid.cpp compiled "
+            "where they lie, Eigen-subset shim, g++ -O2 -ffp-contract=off) on operators assembled by the CPU oracle's threaded set-up (bit-identical to "
+            "the reference's own assembly, whose brute-force kNN is O(N^2))" if kind == "reference" else
+            "CPU oracle (the reference's grid.cpp / multigrid.cpp restated, pinned bit-identical to the reference sources; g++ -O2 -ffp-contract=off)")
+    sample = ("%s, MEASURED on the stated %dx%d hierarchy %s: lexicographic SOR omega=1.4, V-cycle loop on 1 thread because the "
               "reference is serial (%d host cores present); set-up %.0f s on %d threads, untimed; steps = cycles %d..%d of the solve from a zero guess"
-              % (args.side, args.side, sides, cores, setup_s, cores, args.warmup + 1, args.warmup + args.steps))
+              % (what, args.side, args.side, sides, cores, setup_s, cores, args.warmup + 1, args.warmup + args.steps))
     cfg = workload_config(args, sides)
     cfg["smoother"] = "lexicographic SOR omega=1.4 (the reference's own smoother) -- the GPU arm's throughput mode is multicolour SOR omega=%g; compare `solve`" % args.mc_omega
     line = {
@@ -202,7 +224,7 @@ def reference_arm(args):
         "dtype": "f64", "data": "synthetic", "config": cfg,
         "solve": {"tol": TOL, "cycles": len(per_cycle), "seconds": solve_s, "final_residual": r, "converged": bool(r < TOL),
                   "mode": "lexicographic omega=1.4, 1 thread", "convergence_per_cycle": rate},
-        "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": cores, "setup_s": setup_s},
+        "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": 1, "kind": kind, "sample": sample, "host_cores": cores, "setup_s": setup_s},
         "e2e": {"value": v, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -230,6 +252,7 @@ def main():
     ap.add_argument("--mc-omega", type=float, default=0.8, help="relaxation factor of the multicolour (throughput) mode")
     ap.add_argument("--cpu-side", type=int, default=500, help="finest lattice side of the bounded CPU sample")
     ap.add_argument("--cpu-cycles", type=int, default=3)
+    ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port even when oracle/_ref/libref.so (the reference's own sources) is there")
     ap.add_argument("--ref-budget-s", type=float, default=540.0, help="--impl reference: wall budget of the whole arm (set-up included); the solve stops there once "
                                                                        "the W+K cycles are done and is then reported as not converged")
     ap.add_argument("--partition-threshold", type=int, default=200000, help="multi-GPU: levels with fewer rows are replicated")
@@ -417,10 +440,11 @@ def main():
             scale = algorithmic_bytes_per_cycle(r["sides"], args.fine_poly) / algorithmic_bytes_per_cycle(sides, args.fine_poly)
             s_full = r["s_per_cycle"] / scale
             line["cpu_baseline"] = {
-                "value": 1.0 / s_full, "unit": "V-cycles/s", "cores": 1, "kind": "port", "host_cores": cores,
-                "sample": "CPU oracle, lexicographic SOR, %d V-cycles on a %dx%d-side hierarchy %s (%.3f s/cycle measured), scaled by algorithmic "
+                "value": 1.0 / s_full, "unit": "V-cycles/s", "cores": 1, "kind": r["kind"], "host_cores": cores,
+                "sample": "%s, lexicographic SOR, %d V-cycles on a %dx%d-side hierarchy %s (%.3f s/cycle measured), scaled by algorithmic "
                           "bytes x%.4g to the %dx%d workload; set-up used %d threads (%.1f s, untimed)"
-                          % (args.cpu_cycles, args.cpu_side, args.cpu_side, r["sides"], r["s_per_cycle"], 1 / scale, args.side, args.side, cores, r["setup_s"]),
+                          % ("the reference's own Multigrid::vCycle (oracle/_ref/libref.so) on oracle-assembled operators" if r["kind"] == "reference" else "CPU oracle",
+                             args.cpu_cycles, args.cpu_side, args.cpu_side, r["sides"], r["s_per_cycle"], 1 / scale, args.side, args.side, cores, r["setup_s"]),
             }
         print(json.dumps(line))
     if world > 1:

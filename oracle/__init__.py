@@ -369,6 +369,96 @@ class Multigrid:
         return out[:n]
 
 
+REF_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref.so")
+
+
+class ReferenceHierarchy:
+    """The reference's OWN Multigrid / Grid objects (oracle/_ref/libref.so: its grid.cpp and multigrid.cpp compiled where they lie
+    on the Eigen-subset shim) over operators assembled by the oracle.  The reference's set-up is a brute-force kNN -- O(N^2) per
+    level -- so beyond ~100k nodes only its V-cycle can be run as it is; `from_oracle` hands it the matrices of an oracle
+    hierarchy (Dirichlet levels), which are pinned bit-identical to the ones the reference would assemble itself.
+    TEST INFRASTRUCTURE: used by tests/ and by bench.py's reference arm only."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        self.R = R = C.CDLL(REF_SO)
+        dp, ip = np.ctypeslib.ndpointer(np.float64), np.ctypeslib.ndpointer(np.int32)
+        R.ref_new_raw.restype = C.c_void_p
+        R.ref_free.argtypes = [C.c_void_p]
+        R.ref_add_level_raw.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, ip, dp, dp, ip, ip, dp]
+        R.ref_set_interp_raw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, dp]
+        R.ref_time_vcycles.restype = C.c_double
+        R.ref_time_vcycles.argtypes = [C.c_void_p, C.c_int]
+        R.ref_vcycle.argtypes = [C.c_void_p, C.c_int]
+        R.ref_residual.restype = C.c_double
+        R.ref_residual.argtypes = [C.c_void_p]
+        R.ref_history.argtypes = [C.c_void_p, dp, C.c_int]
+        R.ref_lv_vec.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        R.ref_lv_A.argtypes = [C.c_void_p, C.c_int]
+        self.h = C.c_void_p(R.ref_new_raw())
+        self.nlevels = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.ref_free(self.h)
+            self.h = None
+
+    @classmethod
+    def from_oracle(cls, mg):
+        import scipy.sparse as sp
+
+        self = cls()
+        n_lv = mg.nlevels
+        for l in range(n_lv):                                  # ascending size, like addGrid's sort (multigrid.cpp:116-122)
+            lv = mg.level(l)
+            if lv.neumann:
+                raise OracleError("ReferenceHierarchy.from_oracle: Dirichlet levels only")
+            bnd = lv.boundaries()
+            assert len(bnd) == 1 and bnd[0][0] == 1, "one Dirichlet boundary per level (the square of genGmshGridDirichlet)"
+            x, y = lv.points()
+            pr = lv.props
+            (rows, _), ptr, idx, val = lv.csr(MAT_A)
+            assert rows == lv.n
+            self.R.ref_add_level_raw(self.h, lv.n, x, y, pr["polyDeg"], pr["iters"], pr["omega"], pr["rbfExp"], bnd[0][1].size,
+                                     np.ascontiguousarray(bnd[0][1], np.int32), np.ascontiguousarray(bnd[0][2], np.float64), lv.source, ptr, idx, val)
+        self.nlevels = n_lv
+        for l in range(n_lv):                                  # restrictionMatrices_[l]: l >= 1; prolongMatrices_[l]: l < last (multigrid.cpp:34-47)
+            for which, sel, ok in ((0, MAT_R, l >= 1), (1, MAT_P, l < n_lv - 1)):
+                if not ok:
+                    continue
+                shape, ptr, idx, val = mg.level(l).csr(sel)
+                m = sp.csr_matrix((val, idx, ptr), shape=shape).tocsc()     # the reference stores them column-major (multigrid.h:8-9)
+                m.sort_indices()
+                self.R.ref_set_interp_raw(self.h, which, l, shape[0], shape[1], np.ascontiguousarray(m.indptr, np.int32),
+                                          np.ascontiguousarray(m.indices, np.int32), np.ascontiguousarray(m.data, np.float64))
+        return self
+
+    def vcycle(self, n=1):
+        self.R.ref_vcycle(self.h, n)
+
+    def time_vcycles(self, n):
+        """seconds (steady_clock) around n calls of the reference's Multigrid::vCycle, the loop of testing_functions.cpp:340-344"""
+        return self.R.ref_time_vcycles(self.h, n)
+
+    def residual(self):
+        return self.R.ref_residual(self.h)
+
+    def history(self):
+        n = self.R.ref_history(self.h, np.empty(1), 0)
+        out = np.empty(max(n, 1))
+        self.R.ref_history(self.h, out, n)
+        return out[:n]
+
+    def values(self, l=-1):
+        l = l + self.nlevels if l < 0 else l
+        v = np.empty(self.R.ref_lv_A(self.h, l))
+        self.R.ref_lv_vec(self.h, l, 0, v)
+        return v
+
+
 def make_hierarchy(sizes, kind=KIND_DIRICHLET, fine_poly=4, coarse_poly=3, fracstep=False, cells=True, seed0=1000, jitter=0.3, cloud="jittered", geom=0, **kw):
     """The reference's run_mg_sim set-up (testing_functions.cpp:328-339) on synthetic jittered
     lattices: one independent cloud per level, coarse levels polyDeg 3, finest fine_poly."""

@@ -158,6 +158,14 @@ template <class T, int Opt = ColMajor, class I = int> class SparseMatrix {
     return y;
   }
   SparseMatrix scaled(double s) const { SparseMatrix m(*this); for (T& t : m.val_) t = s * t; return m; }
+  // NOT Eigen API (with real Eigen: Eigen::Map<const SparseMatrix>): take over compressed arrays as they are -- outer pointers
+  // (rows for RowMajor, columns for ColMajor), inner indices ascending within an outer slice, values.  Only ref_capi.cpp's raw
+  // injection uses it, to put operators assembled by the oracle's threaded set-up under the reference's own V-cycle.
+  void adoptCompressed(const int* outer, const int* inner, const T* val, Index nnz) {
+    ptr_.assign(outer, outer + (Opt == RowMajor ? r_ : c_) + 1);
+    idx_.assign(inner, inner + nnz);
+    val_.assign(val, val + nnz);
+  }
  private:
   Index r_, c_;
   std::vector<int> ptr_, idx_;

@@ -47,6 +47,57 @@ void* ref_new_geom(int kind, const char* geomtype, int nfiles, const char** file
   if (r->mg) r->mg->buildMatrices(); else r->fmg->buildMatrices();
   return r;
 }
+// ---- the reference's own Multigrid over operators assembled elsewhere (Dirichlet levels).  The reference's set-up is a brute-force
+// kNN, O(N^2) per level and O(N_fine x N_coarse) per interpolation matrix, which rules it out beyond ~100k nodes; its V-cycle
+// (multigrid.cpp:62-110, grid.cpp:104-151) has no such limit.  So bench.py's reference arm assembles with the oracle's threaded
+// set-up (pinned bit-identical to the reference's, test_oracle_is_bit_identical_to_the_reference_sources) and hands the matrices
+// to unmodified reference objects: every cycle that is timed runs the reference's own code.
+void* ref_new_raw() {
+  Ref* r = new Ref();
+  r->mg = new Multigrid();
+  return r;
+}
+void ref_free(void* h) {
+  Ref* r = (Ref*)h;
+  if (r->mg) {   // ~Multigrid deletes prolongMatrices_.at(i) / restrictionMatrices_.at(i) for every grid (multigrid.cpp:10-16)
+    r->mg->prolongMatrices_.resize(r->mg->grids_.size(), nullptr);
+    r->mg->restrictionMatrices_.resize(r->mg->grids_.size(), nullptr);
+    delete r->mg;
+  }
+  delete r->fmg;
+  delete r;
+}
+// one Dirichlet level: points, ONE boundary (ids + values), properties, source_, laplaceMat_ as CSR with ascending columns
+void ref_add_level_raw(void* h, int n, const double* x, const double* y, int polyDeg, int iters, double omega, int rbfExp, int nb, const int* bpts,
+                       const double* bvals, const double* source, const int* ptr, const int* idx, const double* val) {
+  Ref* r = (Ref*)h;
+  std::vector<Point> pts(n);
+  for (int i = 0; i < n; i++) pts[i] = Point(x[i], y[i], 0.0);
+  Boundary b;
+  b.type = 1;
+  b.bcPoints.assign(bpts, bpts + nb);
+  b.values.assign(bvals, bvals + nb);
+  GridProperties p;
+  p.rbfExp = rbfExp; p.polyDeg = polyDeg; p.iters = iters; p.omega = omega; p.laplaceMatSize = n;
+  p.stencilSize = (int)(2.5 * (polyDeg + 1) * (polyDeg + 2) / 2);
+  Eigen::VectorXd src(n);
+  for (int i = 0; i < n; i++) src(i) = source[i];
+  Grid* g = new Grid(pts, std::vector<Boundary>{b}, p, src);
+  g->implicitFlag_ = false;
+  g->setBCFlag(0, std::string("dirichlet"), b.values);       // genGmshGridDirichlet, testing_functions.cpp:150-152
+  g->laplaceMat_->adoptCompressed(ptr, idx, val, ptr[n]);    // in place of rcm_order_points() + build_laplacian()
+  r->mg->addGrid(g);
+}
+// restrictionMatrices_[level] (which 0) / prolongMatrices_[level] (which 1): column-major like the reference's (multigrid.h:8-9)
+void ref_set_interp_raw(void* h, int which, int level, int rows, int cols, const int* colptr, const int* rowidx, const double* val) {
+  Ref* r = (Ref*)h;
+  auto& vec = which == 0 ? r->mg->restrictionMatrices_ : r->mg->prolongMatrices_;
+  vec.resize(r->mg->grids_.size(), nullptr);
+  auto* M = new Eigen::SparseMatrix<double>(rows, cols);
+  M->adoptCompressed(colptr, rowidx, val, colptr[cols]);
+  delete vec.at(level);
+  vec.at(level) = M;
+}
 void ref_vcycle(void* h, int n) {
   Quiet q;
   Ref* r = (Ref*)h;

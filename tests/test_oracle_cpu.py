@@ -114,6 +114,27 @@ def test_oracle_is_bit_identical_to_the_reference_sources(kind, fine_poly, geom)
         assert np.array_equal(u2, mg.level(-1).vec(oracle.VEC_U))
 
 
+def test_reference_objects_on_oracle_operators_cycle_bit_identically():
+    """bench.py's reference arm: the reference's own Multigrid / Grid objects (libref.so) fed with the oracle's matrices
+    (ReferenceHierarchy.from_oracle -- the reference's brute-force set-up is out of reach at 4M nodes) must cycle exactly like
+    the oracle and like the reference built by its own factories."""
+    _ref_lib()
+    if not oracle.ReferenceHierarchy.available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    for sizes, poly in (([13, 25, 40], 4), ([16, 32, 63], 6)):
+        mg = oracle.make_hierarchy(sizes, kind=oracle.KIND_DIRICHLET, fine_poly=poly)
+        ref = oracle.ReferenceHierarchy.from_oracle(mg)
+        assert ref.residual() == mg.residual() == 1.0
+        assert ref.time_vcycles(5) > 0
+        mg.vcycle(5)
+        assert np.array_equal(ref.history(), mg.history())
+        assert np.array_equal(ref.values(), mg.level(-1).values)
+        assert ref.residual() == mg.residual() < 0.2
+    neu = oracle.make_hierarchy([13, 25], kind=oracle.KIND_NEUMANN, fine_poly=3)
+    with pytest.raises(oracle.OracleError):
+        oracle.ReferenceHierarchy.from_oracle(neu)        # Dirichlet levels only
+
+
 # ---------------------------------------------------------------- golden vectors
 @pytest.mark.parametrize("name", ["dirichlet_p4", "dirichlet_p6", "mixed_p4", "neumann_p3"])
 def test_oracle_reproduces_golden_vectors(name):
