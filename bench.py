@@ -193,6 +193,10 @@ def reference_arm(args):
         except (OSError, AttributeError, oracle.OracleError) as e:               # a libref.so that does not load or predates the raw entry points
             print("bench.py: reference objects unavailable (%s); timing the oracle port" % e, file=sys.stderr)
     setup_s = time.time() - t0
+    try:                                           # the timed loop is one thread on one core (`taskset -c`), the last one this process may use
+        os.sched_setaffinity(0, {max(os.sched_getaffinity(0))})
+    except (AttributeError, OSError):
+        pass
     per_cycle, t_solve0 = [], time.perf_counter()
     budget_s = max(0.0, args.ref_budget_s - setup_s)
     r = mg.residual()
@@ -214,7 +218,7 @@ def reference_arm(args):
             "the reference's own assembly, whose brute-force kNN is O(N^2))" if kind == "reference" else
             "CPU oracle (the reference's grid.cpp / multigrid.cpp restated, pinned bit-identical to the reference sources; g++ -O2 -ffp-contract=off)")
     sample = ("%s, MEASURED on the stated %dx%d hierarchy %s: lexicographic SOR omega=1.4, V-cycle loop on 1 thread because the "
-              "reference is serial (%d host cores present); set-up %.0f s on %d threads, untimed; steps = cycles %d..%d of the solve from a zero guess"
+              "reference is serial, pinned to one core (%d host cores present); set-up %.0f s on %d threads, untimed; steps = cycles %d..%d of the solve from a zero guess"
               % (what, args.side, args.side, sides, cores, setup_s, cores, args.warmup + 1, args.warmup + args.steps))
     cfg = workload_config(args, sides)
     cfg["smoother"] = "lexicographic SOR omega=1.4 (the reference's own smoother) -- the GPU arm's throughput mode is multicolour SOR omega=%g; compare `solve`" % args.mc_omega
